@@ -1,0 +1,81 @@
+"""ctypes binding of libbbb.so (include/bbb.h).  There is NO fallback: if the shared library is
+missing or a call fails, a RuntimeError is raised -- the CUDA path is the only path."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbbb.so')
+
+# flags (include/bbb.h)
+F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX = 1, 2, 4, 8, 16, 32, 64
+PRIOR_GAUSSIAN, PRIOR_MIXTURE = 0, 1
+
+
+class Rng(C.Structure):
+    _fields_ = [('seed', C.c_uint64), ('step', C.c_uint32), ('sample_base', C.c_uint32),
+                ('layer', C.c_uint32), ('step_dev', C.c_void_p)]
+
+
+class Prior(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('pi', C.c_float), ('sigma1', C.c_float), ('sigma2', C.c_float)]
+
+
+P, I64, I32, F32, U32, U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint32, C.c_uint64
+_SIGS = {
+    'bbb_version': ([], C.c_int),
+    'bbb_last_error_string': ([], C.c_char_p),
+    'bbb_linear_fwd': ([P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, P, P, P, P], C.c_int),
+    'bbb_linear_bwd': ([P, P, P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, F32, F32, P, P, I64, P,
+                        P, P, P, P, P, P], C.c_int),
+    'bbb_lr_linear_fwd': ([P, I64, P, P, P, P, P, P, P, F32, I64, I64, I64, I64, I32, P, P, P, P], C.c_int),
+    'bbb_lr_linear_bwd': ([P, P, P, I64, P, P, P, P, P, P, P, P, F32, I64, I64, I64, I64, I32, F32, P, P,
+                           P, P, P, P, P, P], C.c_int),
+    'bbb_logprob_reduce': ([P, P, P, U64, U32, U32, U32, P, I64, I32, P, P, P, P], C.c_int),
+    'bbb_kl_gauss': ([P, P, F32, I64, P, P], C.c_int),
+    'bbb_philox_fill_normal': ([P, I64, U64, U32, U32, U32, P], C.c_int),
+    'bbb_nll_ce': ([P, P, I64, I64, I64, F32, P, P, P], C.c_int),
+    'bbb_nll_gauss': ([P, P, F32, I64, I64, I64, F32, P, P, P], C.c_int),
+    'bbb_elbo_finalize': ([P, P, P, P, I64, F32, P, P], C.c_int),
+    'bbb_counter_add': ([P, U32, P], C.c_int),
+}
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+
+
+def lib():
+    """Load libbbb.so once.  Raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; '
+                               f'g.build()"` (nvcc, sm_100a).  There is no CPU or PyTorch fallback.')
+        l = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.argtypes, fn.restype = argtypes, restype
+        _lib = l
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError(f'{what} failed ({status}): {lib().bbb_last_error_string().decode()}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('bayesian-neural-network_b200 runs on CUDA tensors only (sm_100a kernels, no CPU '
+                               'fallback); move the module and its inputs to a cuda device')

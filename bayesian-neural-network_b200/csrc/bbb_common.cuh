@@ -1,0 +1,228 @@
+// Shared device math for the BBB kernels: Philox4x32-10 eps stream, softplus, prior/posterior
+// log-densities and their derivatives, block reductions, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bbb.h"
+
+namespace bbb {
+
+// ---------------------------------------------------------------------------------------
+// error plumbing (thread-local message, integer status; never throws)
+// ---------------------------------------------------------------------------------------
+char *last_error_buf();
+int fail(int code, const char *fmt, ...);
+#define BBB_CHECK_ARG(cond, msg)                                         \
+  do {                                                                   \
+    if (!(cond)) return ::bbb::fail(BBB_EINVAL, "%s: %s", __func__, msg); \
+  } while (0)
+#define BBB_CHECK_LAUNCH()                                                                        \
+  do {                                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess) return ::bbb::fail(BBB_ECUDA, "%s: %s", __func__, cudaGetErrorString(e__)); \
+  } while (0)
+#define BBB_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) return ::bbb::fail(BBB_ECUDA, "%s: %s", __func__, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// constants
+// ---------------------------------------------------------------------------------------
+constexpr float kHalfLog2Pi = 0.918938533204672741780329736406f;
+constexpr int kSMs = 148;  // B200
+
+// Prior descriptor with the per-call constants folded on the host.
+struct PriorDev {
+  int kind;
+  float c1, k1, inv_var1;  // component 1: log(pi) - log(s1) - .5log2pi ; 1/(2 s1^2) ; 1/s1^2
+  float c2, k2, inv_var2;  // component 2 (mixture only)
+};
+
+inline PriorDev make_prior_dev(const bbb_prior *p) {
+  PriorDev d{};
+  d.kind = p->kind;
+  if (p->kind == BBB_PRIOR_MIXTURE) {
+    double s1 = p->sigma1, s2 = p->sigma2, pi = p->pi;
+    d.c1 = (float)(log(pi) - log(s1) - 0.918938533204672741780329736406);
+    d.c2 = (float)(log1p(-pi) - log(s2) - 0.918938533204672741780329736406);
+    d.k1 = (float)(1.0 / (2.0 * s1 * s1));
+    d.k2 = (float)(1.0 / (2.0 * s2 * s2));
+    d.inv_var1 = (float)(1.0 / (s1 * s1));
+    d.inv_var2 = (float)(1.0 / (s2 * s2));
+  } else {
+    double s1 = p->sigma1;
+    d.c1 = (float)(-log(s1) - 0.918938533204672741780329736406);
+    d.k1 = (float)(1.0 / (2.0 * s1 * s1));
+    d.inv_var1 = (float)(1.0 / (s1 * s1));
+  }
+  return d;
+}
+
+struct RngDev {
+  uint32_t key0, key1;  // seed
+  uint32_t step;
+  uint32_t sample_base;
+  uint32_t tensor_w, tensor_b;
+  const uint32_t *step_dev;
+};
+
+inline RngDev make_rng_dev(const bbb_rng *r) {
+  RngDev d{};
+  if (r) {
+    d.key0 = (uint32_t)(r->seed & 0xffffffffu);
+    d.key1 = (uint32_t)(r->seed >> 32);
+    d.step = r->step;
+    d.sample_base = r->sample_base;
+    d.tensor_w = 2u * r->layer;
+    d.tensor_b = 2u * r->layer + 1u;
+    d.step_dev = r->step_dev;
+  }
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011) -> 4 standard normals by Box-Muller.
+// counter = (quad index, global sample, tensor id, step); key = seed.  The mapping depends only
+// on the element's linear index, never on the tiling, so forward and backward regenerate
+// bit-identical eps.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1]
+  return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &z0, float &z1) {
+  float u = u32_to_unit(a), v = u32_to_unit(b);
+  float r = sqrtf(-2.0f * logf(u));
+  float s, c;
+  sincospif(2.0f * v, &s, &c);
+  z0 = r * s;
+  z1 = r * c;
+}
+
+// fold the optional device-side step counter into the by-value descriptor (call once per thread)
+__device__ __forceinline__ void rng_resolve(RngDev &rng) {
+  if (rng.step_dev) rng.step += __ldg(rng.step_dev);
+}
+
+// 4 normals for elements 4q..4q+3 of tensor `tensor`, global sample `sample`.
+__device__ __forceinline__ void philox_normal4(const RngDev &rng, uint32_t tensor, uint32_t sample,
+                                               uint32_t quad, float z[4]) {
+  uint4 r = philox4x32_10(quad, sample, tensor, rng.step, rng.key0, rng.key1);
+  box_muller(r.x, r.y, z[0], z[1]);
+  box_muller(r.z, r.w, z[2], z[3]);
+}
+
+// one normal for linear element index e (slow path for rows that are not 16-byte aligned)
+__device__ __forceinline__ float philox_normal1(const RngDev &rng, uint32_t tensor, uint32_t sample,
+                                                uint64_t e) {
+  uint4 r = philox4x32_10((uint32_t)(e >> 2), sample, tensor, rng.step, rng.key0, rng.key1);
+  uint32_t lane = (uint32_t)(e & 3u);
+  float z0, z1;
+  if (lane < 2) box_muller(r.x, r.y, z0, z1);
+  else box_muller(r.z, r.w, z0, z1);
+  return (lane & 1u) ? z1 : z0;
+}
+
+// ---------------------------------------------------------------------------------------
+// posterior / prior math
+// ---------------------------------------------------------------------------------------
+// sigma = log(1 + e^rho)  (networks.py:39).  Above rho = 15 the algebraically identical
+// rho + log1p(e^-rho) is used, which stays finite where the reference overflows (SURVEY B-6).
+__device__ __forceinline__ float softplus_f(float rho) {
+  return rho > 15.0f ? rho + log1pf(expf(-rho)) : log1pf(expf(rho));
+}
+__device__ __forceinline__ float sigmoid_f(float rho) { return 1.0f / (1.0f + expf(-rho)); }
+
+// log q contribution of one element: -0.5 log 2pi - log sigma - eps^2 / 2   (networks.py:46)
+__device__ __forceinline__ float logq_elem(float sigma, float eps) {
+  return -kHalfLog2Pi - logf(sigma) - 0.5f * eps * eps;
+}
+
+// log p(w) of one element (stable log-sum-exp form of networks.py:24-27, or networks.py:67-68)
+__device__ __forceinline__ float logp_elem(const PriorDev &p, float w) {
+  float w2 = w * w;
+  float a = fmaf(-p.k1, w2, p.c1);
+  if (p.kind == BBB_PRIOR_GAUSSIAN) return a;
+  float b = fmaf(-p.k2, w2, p.c2);
+  float m = fmaxf(a, b);
+  return m + logf(expf(a - m) + expf(b - m));
+}
+
+// R(w) with d log p / d w = -w R(w): responsibilities-weighted inverse variance
+__device__ __forceinline__ float prior_R(const PriorDev &p, float w) {
+  if (p.kind == BBB_PRIOR_GAUSSIAN) return p.inv_var1;
+  float w2 = w * w;
+  float a = fmaf(-p.k1, w2, p.c1), b = fmaf(-p.k2, w2, p.c2);
+  float m = fmaxf(a, b);
+  float ea = expf(a - m), eb = expf(b - m);
+  float inv = 1.0f / (ea + eb);
+  return (ea * p.inv_var1 + eb * p.inv_var2) * inv;
+}
+
+// ---------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of two floats, result added to two double accumulators by one thread.
+// `red` is a __shared__ float[2*32] scratch.  All threads of the block must call.
+__device__ __forceinline__ void block_sum2_atomic(float a, float b, float *red, double *dst_a,
+                                                  double *dst_b) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
+  __syncthreads();
+  if (warp == 0) {
+    double da = lane < nwarp ? (double)red[lane] : 0.0;
+    double db = lane < nwarp ? (double)red[32 + lane] : 0.0;
+    da = warp_sum_d(da);
+    db = warp_sum_d(db);
+    if (lane == 0) {
+      if (dst_a) atomicAdd(dst_a, da);
+      if (dst_b) atomicAdd(dst_b, db);
+    }
+  }
+  __syncthreads();
+}
+
+// 4 consecutive floats starting at base[idx], zero-filled past `valid` elements.
+__device__ __forceinline__ void ld4(const float *__restrict__ base, int64_t idx, int valid, bool vec,
+                                    float v[4]) {
+  if (vec && valid >= 4) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(base + idx));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = j < valid ? __ldg(base + idx + j) : 0.0f;
+  }
+}
+
+}  // namespace bbb

@@ -1,0 +1,61 @@
+// Internal launcher interface between the C-ABI entry points (bbb_api.cu) and the kernel files.
+#pragma once
+#include "bbb_common.cuh"
+
+namespace bbb {
+
+// Arguments of the weight-sampling layer kernels (forward and backward share one struct).
+struct LinArgs {
+  // forward operands
+  const float *x;
+  int64_t x_sstride;
+  const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_w, *eps_b;
+  RngDev rng;
+  PriorDev prior;
+  int S;
+  int64_t B, in, out;
+  int flags;
+  float *y;
+  double *logp, *logq;
+  // backward operands
+  const float *dy, *mask;
+  float gp, gq;
+  const float *gp_dev, *gq_dev;
+  int64_t g_dev_stride;
+  const float *out_scale_dev;
+  float *dx, *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;
+  // derived
+  bool vec_in;   // in % 4 == 0 and every [*, in] base pointer 16-byte aligned
+  bool vec_out;  // out % 4 == 0 and every [*, out] base pointer 16-byte aligned
+};
+
+// Arguments of the local-reparameterisation layer kernels.
+struct LrArgs {
+  const float *x;
+  int64_t x_sstride;
+  const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_a, *eps_b;
+  RngDev rng;
+  float sigma_p;
+  int S;
+  int64_t B, in, out;
+  int flags;
+  float *y, *delta;
+  double *kl;
+  const float *dy, *mask, *delta_in;
+  float g_kl;
+  const float *g_kl_dev, *out_scale_dev;
+  float *dx, *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;
+  bool vec_in, vec_out;
+};
+
+int launch_linear_fwd_fma(const LinArgs &a, cudaStream_t st);
+int launch_linear_bwd_fma(const LinArgs &a, cudaStream_t st);
+int launch_lr_fwd_fma(const LrArgs &a, cudaStream_t st);
+int launch_lr_bwd_fma(const LrArgs &a, cudaStream_t st);
+
+// tcgen05 kind::tf32 path (bbb_linear_tc.cu); returns BBB_EUNSUPPORTED when the shape does not fit.
+bool linear_tc_supported(const LinArgs &a);
+int launch_linear_fwd_tc(const LinArgs &a, cudaStream_t st);
+int launch_linear_bwd_tc(const LinArgs &a, cudaStream_t st);
+
+}  // namespace bbb

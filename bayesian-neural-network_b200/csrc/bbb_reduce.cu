@@ -1,0 +1,276 @@
+// Bandwidth-bound single-pass kernels: ELBO reductions over (mu, rho[, eps]), closed-form KL,
+// the Philox eps stream, likelihood terms and ELBO assembly.
+//
+// Roofline: HBM.  bbb_logprob_reduce reads 8 B/weight (mu, rho; +4 with injected eps, +4 when W is
+// written) and does ~60 flops + Philox per weight; bbb_kl_gauss reads 8 B/weight.  Loads are 16-byte
+// vectors, four independent vectors in flight per thread, grid = a multiple of the 148 SMs.
+#include <stdarg.h>
+
+#include "bbb_common.cuh"
+
+namespace bbb {
+
+// ---- error plumbing ------------------------------------------------------------------
+char *last_error_buf() {
+  static thread_local char buf[512] = "ok";
+  return buf;
+}
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+namespace {
+
+constexpr int RT = 256;  // threads per CTA of the reduction kernels
+
+template <bool kInjected, bool kWriteW>
+__global__ void __launch_bounds__(RT) logprob_reduce_kernel(const float *__restrict__ mu,
+                                                            const float *__restrict__ rho,
+                                                            const float *__restrict__ eps, RngDev rng,
+                                                            uint32_t tensor, uint32_t sample, PriorDev prior,
+                                                            int64_t n, int sample_flag, float *__restrict__ w_out,
+                                                            double *logp, double *logq) {
+  __shared__ float red[64];
+  rng_resolve(rng);
+  float lp = 0.0f, lq = 0.0f;
+  const int64_t nq = n >> 2;  // whole quads
+  const int64_t stride = (int64_t)gridDim.x * RT;
+  for (int64_t q = (int64_t)blockIdx.x * RT + threadIdx.x; q < nq; q += stride) {
+    const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mu) + q);
+    const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rho) + q);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
+    float e[4] = {0.f, 0.f, 0.f, 0.f}, w[4];
+    if (sample_flag) {
+      if (kInjected) {
+        const float4 e4 = __ldg(reinterpret_cast<const float4 *>(eps) + q);
+        e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
+      } else {
+        philox_normal4(rng, tensor, sample, (uint32_t)q, e);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sg = softplus_f(r[j]);
+      w[j] = fmaf(sg, e[j], m[j]);
+      lp += logp_elem(prior, w[j]);
+      lq += logq_elem(sg, e[j]);
+    }
+    if (kWriteW) reinterpret_cast<float4 *>(w_out)[q] = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  // tail (n % 4 elements) handled by the first threads of block 0
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (nq << 2) + threadIdx.x;
+    const float sg = softplus_f(rho[i]);
+    float e = 0.0f;
+    if (sample_flag) e = kInjected ? eps[i] : philox_normal1(rng, tensor, sample, (uint64_t)i);
+    const float w = fmaf(sg, e, mu[i]);
+    lp += logp_elem(prior, w);
+    lq += logq_elem(sg, e);
+    if (kWriteW) w_out[i] = w;
+  }
+  block_sum2_atomic(lp, lq, red, logp, logq);
+}
+
+__global__ void __launch_bounds__(RT) kl_gauss_kernel(const float *__restrict__ mu, const float *__restrict__ rho,
+                                                      float log_sp, float inv_sp2, int64_t n, double *kl) {
+  __shared__ float red[64];
+  float acc = 0.0f;
+  const int64_t nq = n >> 2, stride = (int64_t)gridDim.x * RT;
+  for (int64_t q = (int64_t)blockIdx.x * RT + threadIdx.x; q < nq; q += stride) {
+    const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mu) + q);
+    const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rho) + q);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sg = softplus_f(r[j]);
+      acc += 2.0f * (log_sp - logf(sg)) - 1.0f + (sg * sg + m[j] * m[j]) * inv_sp2;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (nq << 2) + threadIdx.x;
+    const float sg = softplus_f(rho[i]);
+    acc += 2.0f * (log_sp - logf(sg)) - 1.0f + (sg * sg + mu[i] * mu[i]) * inv_sp2;
+  }
+  block_sum2_atomic(0.5f * acc, 0.0f, red, kl, nullptr);
+}
+
+__global__ void __launch_bounds__(RT) philox_fill_kernel(float *__restrict__ out, int64_t n, RngDev rng,
+                                                         uint32_t tensor, uint32_t sample) {
+  const int64_t nq = (n + 3) >> 2, stride = (int64_t)gridDim.x * RT;
+  for (int64_t q = (int64_t)blockIdx.x * RT + threadIdx.x; q < nq; q += stride) {
+    float z[4];
+    philox_normal4(rng, tensor, sample, (uint32_t)q, z);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((q << 2) + j < n) out[(q << 2) + j] = z[j];
+  }
+}
+
+// one warp per (s, b) row of logits
+__global__ void __launch_bounds__(128) nll_ce_kernel(const float *__restrict__ logits,
+                                                     const int64_t *__restrict__ target, int64_t rows, int64_t B,
+                                                     int64_t C, float grad_scale, double *nll,
+                                                     float *__restrict__ dlogits) {
+  __shared__ float red[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float local = 0.0f;
+  for (int64_t row = (int64_t)blockIdx.x * 4 + warp; row < rows; row += (int64_t)gridDim.x * 4) {
+    const float *z = logits + row * C;
+    const int64_t t = target[row % B];
+    float mx = -INFINITY;
+    for (int64_t c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.0f;
+    for (int64_t c = lane; c < C; c += 32) se += expf(z[c] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    if (lane == 0) local += lse - z[t];
+    if (dlogits) {
+      float *g = dlogits + row * C;
+      for (int64_t c = lane; c < C; c += 32) g[c] = grad_scale * (expf(z[c] - lse) - (c == t ? 1.0f : 0.0f));
+    }
+  }
+  block_sum2_atomic(local, 0.0f, red, nll, nullptr);
+}
+
+__global__ void __launch_bounds__(RT) nll_gauss_kernel(const float *__restrict__ out, const float *__restrict__ target,
+                                                       float inv_2var, float inv_var, float cst, int64_t n,
+                                                       int64_t per_sample, float grad_scale, double *nll,
+                                                       float *__restrict__ dout) {
+  __shared__ float red[64];
+  float acc = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * RT + threadIdx.x; i < n; i += (int64_t)gridDim.x * RT) {
+    const float d = out[i] - target[i % per_sample];
+    acc += fmaf(d * d, inv_2var, cst);
+    if (dout) dout[i] = grad_scale * d * inv_var;
+  }
+  block_sum2_atomic(acc, 0.0f, red, nll, nullptr);
+}
+
+__global__ void elbo_finalize_kernel(const double *logp, const double *logq, const double *kl, const double *nll,
+                                     int S, float beta, float *out4) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float nll_m = (float)(nll[0] / S);
+  if (kl) {
+    const float k = (float)kl[0];
+    out4[0] = beta * k + nll_m; out4[1] = k; out4[2] = nll_m; out4[3] = 0.0f;
+  } else {
+    double lp = 0.0, lq = 0.0;
+    for (int s = 0; s < S; ++s) { lp += (double)(float)logp[s]; lq += (double)(float)logq[s]; }
+    const float lpm = (float)(lp / S), lqm = (float)(lq / S);
+    out4[0] = beta * lqm - beta * lpm + nll_m; out4[1] = lpm; out4[2] = lqm; out4[3] = nll_m;
+  }
+}
+
+inline int grid_for(int64_t work_items, int per_cta) {
+  int64_t need = (work_items + per_cta - 1) / per_cta;
+  int64_t cap = (int64_t)kSMs * 8;  // 8 resident CTAs of 256 threads per SM
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace bbb
+
+using namespace bbb;
+
+extern "C" int bbb_logprob_reduce(const float *mu, const float *rho, const float *eps, uint64_t seed, uint32_t step,
+                                  uint32_t sample, uint32_t tensor_id, const bbb_prior *prior, int64_t n,
+                                  int32_t flags, float *w_out, double *logp, double *logq, void *stream) {
+  BBB_CHECK_ARG(mu && rho && prior && logp && logq, "null pointer");
+  BBB_CHECK_ARG(n >= 0, "negative size");
+  BBB_CHECK_ARG(aligned16(mu) && aligned16(rho) && (!eps || aligned16(eps)) && (!w_out || aligned16(w_out)),
+                "pointers must be 16-byte aligned");
+  if (n == 0) return BBB_OK;
+  bbb_rng r{seed, step, 0, 0, nullptr};
+  RngDev rng = make_rng_dev(&r);
+  PriorDev pd = make_prior_dev(prior);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(n >> 2, RT * 4);
+  const int sf = (flags & BBB_F_SAMPLE) ? 1 : 0;
+#define LAUNCH(INJ, WR) \
+  logprob_reduce_kernel<INJ, WR><<<grid, RT, 0, st>>>(mu, rho, eps, rng, tensor_id, sample, pd, n, sf, w_out, logp, logq)
+  if (eps && w_out) LAUNCH(true, true);
+  else if (eps) LAUNCH(true, false);
+  else if (w_out) LAUNCH(false, true);
+  else LAUNCH(false, false);
+#undef LAUNCH
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+extern "C" int bbb_kl_gauss(const float *mu, const float *rho, float sigma_p, int64_t n, double *kl, void *stream) {
+  BBB_CHECK_ARG(mu && rho && kl, "null pointer");
+  BBB_CHECK_ARG(n >= 0 && sigma_p > 0, "bad size or sigma_p");
+  BBB_CHECK_ARG(aligned16(mu) && aligned16(rho), "pointers must be 16-byte aligned");
+  if (n == 0) return BBB_OK;
+  kl_gauss_kernel<<<grid_for(n >> 2, RT * 4), RT, 0, (cudaStream_t)stream>>>(
+      mu, rho, logf(sigma_p), 1.0f / (sigma_p * sigma_p), n, kl);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+extern "C" int bbb_philox_fill_normal(float *out, int64_t n, uint64_t seed, uint32_t step, uint32_t sample,
+                                      uint32_t tensor_id, void *stream) {
+  BBB_CHECK_ARG(out && n >= 0, "null pointer or negative size");
+  if (n == 0) return BBB_OK;
+  bbb_rng r{seed, step, 0, 0, nullptr};
+  philox_fill_kernel<<<grid_for((n + 3) >> 2, RT * 4), RT, 0, (cudaStream_t)stream>>>(out, n, make_rng_dev(&r),
+                                                                                    tensor_id, sample);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+extern "C" int bbb_nll_ce(const float *logits, const int64_t *target, int64_t S, int64_t B, int64_t C,
+                          float grad_scale, double *nll, float *dlogits, void *stream) {
+  BBB_CHECK_ARG(logits && target && nll, "null pointer");
+  BBB_CHECK_ARG(S >= 0 && B >= 0 && C > 0, "bad shape");
+  const int64_t rows = S * B;
+  if (rows == 0) return BBB_OK;
+  nll_ce_kernel<<<grid_for(rows, 4), 128, 0, (cudaStream_t)stream>>>(logits, target, rows, B, C, grad_scale, nll,
+                                                                     dlogits);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+extern "C" int bbb_nll_gauss(const float *out, const float *target, float sigma, int64_t S, int64_t B, int64_t D,
+                             float grad_scale, double *nll, float *dout, void *stream) {
+  BBB_CHECK_ARG(out && target && nll, "null pointer");
+  BBB_CHECK_ARG(S >= 0 && B >= 0 && D >= 0 && sigma > 0, "bad shape or sigma");
+  const int64_t n = S * B * D;
+  if (n == 0) return BBB_OK;
+  const double var = (double)sigma * sigma;
+  nll_gauss_kernel<<<grid_for(n, RT), RT, 0, (cudaStream_t)stream>>>(
+      out, target, (float)(0.5 / var), (float)(1.0 / var), (float)(log((double)sigma) + 0.918938533204672741780329736406),
+      n, B * D, grad_scale, nll, dout);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+extern "C" int bbb_elbo_finalize(const double *logp, const double *logq, const double *kl, const double *nll,
+                                 int64_t S, float beta, float *out4, void *stream) {
+  BBB_CHECK_ARG(nll && out4 && S > 0, "null pointer or S <= 0");
+  BBB_CHECK_ARG(kl || (logp && logq), "need kl or logp+logq");
+  elbo_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(logp, logq, kl, nll, (int)S, beta, out4);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+namespace bbb { namespace {
+__global__ void counter_add_kernel(uint32_t *c, uint32_t inc) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += inc; }
+} }
+extern "C" int bbb_counter_add(uint32_t *counter, uint32_t inc, void *stream) {
+  BBB_CHECK_ARG(counter, "null pointer");
+  counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, inc);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+extern "C" int bbb_version(void) { return BBB_VERSION; }
+extern "C" const char *bbb_last_error_string(void) { return last_error_buf(); }

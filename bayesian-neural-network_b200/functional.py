@@ -1,0 +1,539 @@
+"""torch.autograd glue between the nn.Module mirror of the reference API and the C-ABI kernels.
+
+Every function here launches libbbb.so kernels on the current CUDA stream through ctypes
+(_lib.py); PyTorch only owns the buffers and the autograd tape.  Nothing here computes on
+the CPU and nothing imports oracle/.
+
+Layer level  : bayes_linear / lr_linear          (one launch fwd, two bwd; S = 1)
+Network level: mlp_forward / mlp_forward_lr      (all S samples per launch, ReLU fused into the
+                                                  consumer's operand load, differentiable outputs)
+               fused_elbo / fused_elbo_lr        (the above + likelihood + ELBO assembly, loss only
+                                                  differentiable: what sample_elbo[_lr] call)
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import rng as R
+
+
+def make_prior(prior_init, mixture_prior):
+    """prior_init -> bbb_prior (networks.py:61-68; mixture sigmas are exp(log sigma))."""
+    import math
+    if mixture_prior:
+        assert len(prior_init) == 3, "Scale Mixture Prior requires three values in prior initialisation"
+        return L.Prior(L.PRIOR_MIXTURE, float(prior_init[0]), math.exp(prior_init[1]), math.exp(prior_init[2]))
+    assert len(prior_init) == 1, "Gaussian Prior requires one value in prior initialisation"
+    return L.Prior(L.PRIOR_GAUSSIAN, 0.0, float(prior_init[0]), 0.0)
+
+
+def _rng(layer, seed, step):
+    dev = R.device_step()
+    return L.Rng(seed, step, R.get_sample_base(), layer, L.ptr(dev))
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _EpsPlan:
+    """eps for one call: injected tensors (reference mode) or Philox coordinates."""
+
+    def __init__(self, injected=None, seed=0, step=0):
+        self.injected, self.seed, self.step = injected, seed, step
+
+    def ptrs(self, l):
+        if self.injected is None:
+            return None, None
+        return L.ptr(self.injected[l][0]), L.ptr(self.injected[l][1])
+
+    def rng(self, l):
+        return _rng(l, self.seed, self.step)
+
+    def tensors(self):
+        return [] if self.injected is None else [t for pair in self.injected.values() for t in pair]
+
+
+def plan_eps(shapes, S, device, sample=True):
+    """shapes: per layer (shape of the weight-like eps, shape of the bias eps).  In reference mode the
+    draws follow SURVEY App. A-4: for s: for layer: weight eps, bias eps."""
+    if not sample:
+        return _EpsPlan()
+    if R.get_eps_mode() == 'reference':
+        per = [([], []) for _ in shapes]
+        for _ in range(S):
+            for l, (sw, sb) in enumerate(shapes):
+                per[l][0].append(torch.randn(sw))
+                per[l][1].append(torch.randn(sb))
+        inj = {l: (torch.stack(a).to(device), torch.stack(b).to(device)) for l, (a, b) in enumerate(per)}
+        return _EpsPlan(inj)
+    seed, step = R.next_step()
+    return _EpsPlan(None, seed, step)
+
+
+# =========================================================================================
+# weight-sampling kernels: host-side launch helpers
+# =========================================================================================
+def _ws_fwd(x, x_stride, p, eps, l, prior, S, B, flags, y, logp, logq):
+    wm, wr, bm, br = p
+    out, inn = wm.shape
+    ew, eb = eps.ptrs(l)
+    rng = eps.rng(l)
+    L.check(L.lib().bbb_linear_fwd(L.ptr(x), x_stride, L.ptr(wm), L.ptr(wr), L.ptr(bm), L.ptr(br), ew, eb,
+                                   C.byref(rng), C.byref(prior), S, B, inn, out, flags, L.ptr(y),
+                                   L.ptr(logp), L.ptr(logq), L.stream()), 'bbb_linear_fwd')
+
+
+def _ws_bwd(dy, mask, x, x_stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev, gq_dev, g_stride, out_scale, dx,
+            grads):
+    wm, wr, bm, br = p
+    out, inn = wm.shape
+    ew, eb = eps.ptrs(l)
+    rng = eps.rng(l)
+    L.check(L.lib().bbb_linear_bwd(L.ptr(dy), L.ptr(mask), L.ptr(x), x_stride, L.ptr(wm), L.ptr(wr), L.ptr(bm),
+                                   L.ptr(br), ew, eb, C.byref(rng), C.byref(prior), S, B, inn, out, flags,
+                                   gp, gq, L.ptr(gp_dev), L.ptr(gq_dev), g_stride, L.ptr(out_scale), L.ptr(dx),
+                                   L.ptr(grads[0]), L.ptr(grads[1]), L.ptr(grads[2]), L.ptr(grads[3]),
+                                   L.stream()), 'bbb_linear_bwd')
+
+
+def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq):
+    """All layers, all S samples.  Returns the list of pre-activation outputs ys[l] = [S,B,out_l]."""
+    B = x2.shape[0]
+    ys = []
+    base = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if logprob else 0) | (L.F_TF32 if tf32 else 0)
+    inp, stride = x2, 0
+    for l, p in enumerate(params):
+        out, inn = p[0].shape
+        y = torch.empty((S, B, out), dtype=torch.float32, device=x2.device)
+        _ws_fwd(inp, stride, p, eps, l, prior, S, B, base | (L.F_RELU_IN if l > 0 else 0), y, logp, logq)
+        ys.append(y)
+        inp, stride = y, B * out
+    return ys
+
+
+def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq, gp_dev, gq_dev, g_stride,
+                     out_scale, need_dx0):
+    """Backward of _net_ws_forward.  Returns (dx0 or None, [grads per layer])."""
+    B = x2.shape[0]
+    base = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0)
+    grads = [None] * len(params)
+    dy, dx0 = d_out, None
+    for l in reversed(range(len(params))):
+        p = params[l]
+        out, inn = p[0].shape
+        g = tuple(torch.empty_like(t) for t in p)
+        flags = base | (L.F_RELU_IN if l > 0 else 0)
+        want_dx = l > 0 or need_dx0
+        dx = torch.empty((S, B, inn), dtype=torch.float32, device=x2.device) if want_dx else None
+        if not want_dx:
+            flags |= L.F_NO_DX
+        if l == 0 and need_dx0:
+            flags |= L.F_SCALE_DX
+        mask = ys[l] if l + 1 < len(params) else None
+        x_in, stride = (x2, 0) if l == 0 else (ys[l - 1], B * inn)
+        _ws_bwd(dy, mask, x_in, stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev, gq_dev, g_stride, out_scale,
+                dx, g)
+        grads[l] = g
+        dy = dx
+        if l == 0:
+            dx0 = dx
+    return dx0, grads
+
+
+# =========================================================================================
+# layer level
+# =========================================================================================
+class _BayesLinear(torch.autograd.Function):
+    """BayesianLinear.forward for one sample (networks.py:73-88) -> (y, log_prior, log_post)."""
+
+    @staticmethod
+    def forward(ctx, x, wm, wr, bm, br, prior, sample, logprob, layer_id, tf32):
+        L.require_cuda(x, wm, wr, bm, br)
+        out, inn = wm.shape
+        x2 = _f32c(x).reshape(-1, inn)
+        B = x2.shape[0]
+        p = tuple(_f32c(t) for t in (wm, wr, bm, br))
+        eps = plan_eps([((out, inn), (out,))], 1, x2.device, sample)
+        if eps.injected is not None:            # re-key as layer `layer_id`
+            eps.injected = {layer_id: eps.injected[0]}
+        acc = torch.zeros(2, dtype=torch.float64, device=x2.device)
+        y = torch.empty((1, B, out), dtype=torch.float32, device=x2.device)
+        flags = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if logprob else 0) | (L.F_TF32 if tf32 else 0)
+        _ws_fwd(x2, 0, p, eps, layer_id, prior, 1, B, flags, y, acc[0:1], acc[1:2])
+        ctx.save_for_backward(x2, *p, *eps.tensors())
+        ctx.cfg = (prior, sample, logprob, layer_id, tf32, eps, x.shape, x.requires_grad)
+        ctx.set_materialize_grads(False)
+        lpq = acc.to(torch.float32)
+        return y.view(*x.shape[:-1], out), lpq[0], lpq[1]
+
+    @staticmethod
+    def backward(ctx, dy, dlp, dlq):
+        prior, sample, logprob, layer_id, tf32, eps, xshape, x_rg = ctx.cfg
+        x2, wm, wr, bm, br = ctx.saved_tensors[:5]
+        out, inn = wm.shape
+        B = x2.shape[0]
+        if dy is None:
+            dy = torch.zeros((B, out), dtype=torch.float32, device=x2.device)
+        dy = _f32c(dy).reshape(1, B, out)
+        g = tuple(torch.empty_like(t) for t in (wm, wr, bm, br))
+        dx = torch.empty((1, B, inn), dtype=torch.float32, device=x2.device) if x_rg else None
+        flags = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0) | (0 if x_rg else L.F_NO_DX)
+        gp_dev = _f32c(dlp).reshape(1) if dlp is not None else None
+        gq_dev = _f32c(dlq).reshape(1) if dlq is not None else None
+        _ws_bwd(dy, None, x2, 0, (wm, wr, bm, br), eps, layer_id, prior, 1, B, flags,
+                1.0 if gp_dev is not None else 0.0, 1.0 if gq_dev is not None else 0.0, gp_dev, gq_dev, 0, None, dx, g)
+        return (dx.view(xshape) if x_rg else None, g[0], g[1], g[2], g[3], None, None, None, None, None)
+
+
+def bayes_linear(x, wm, wr, bm, br, prior, sample, logprob, layer_id=0, tf32=False):
+    return _BayesLinear.apply(x, wm, wr, bm, br, prior, sample, logprob, layer_id, tf32)
+
+
+# =========================================================================================
+# network level, weight sampling
+# =========================================================================================
+class _MLPForward(torch.autograd.Function):
+    """S sampled forwards of the whole MLP: (x, params) -> outputs [S,B,C], log_prior [S], log_post [S]."""
+
+    @staticmethod
+    def forward(ctx, x2, prior, S, sample, logprob, tf32, *flat):
+        L.require_cuda(x2, *flat)
+        x2 = _f32c(x2)
+        params = [tuple(_f32c(t) for t in flat[i:i + 4]) for i in range(0, len(flat), 4)]
+        eps = plan_eps([(tuple(p[0].shape), (p[0].shape[0],)) for p in params], S, x2.device, sample)
+        acc = torch.zeros(2 * S, dtype=torch.float64, device=x2.device)
+        ys = _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, acc[:S], acc[S:])
+        ctx.save_for_backward(x2, *flat, *ys, *eps.tensors())
+        ctx.cfg = (prior, S, sample, tf32, eps, len(params), x2.requires_grad)
+        ctx.set_materialize_grads(False)
+        lpq = acc.to(torch.float32)
+        # the last layer's buffer is handed out; backward only needs the hidden pre-activations
+        return ys[-1], lpq[:S], lpq[S:]
+
+    @staticmethod
+    def backward(ctx, d_out, dlp, dlq):
+        prior, S, sample, tf32, eps, nl, x_rg = ctx.cfg
+        sv = ctx.saved_tensors
+        x2 = sv[0]
+        params = [tuple(_f32c(t) for t in sv[1 + 4 * i:5 + 4 * i]) for i in range(nl)]
+        ys = list(sv[1 + 4 * nl:1 + 5 * nl])
+        B = x2.shape[0]
+        if d_out is None:
+            d_out = torch.zeros_like(ys[-1])
+        gp_dev = _f32c(dlp) if dlp is not None else None
+        gq_dev = _f32c(dlq) if dlq is not None else None
+        dx0, grads = _net_ws_backward(x2, ys, _f32c(d_out), params, prior, S, eps, sample, tf32,
+                                      1.0 if gp_dev is not None else 0.0, 1.0 if gq_dev is not None else 0.0,
+                                      gp_dev, gq_dev, 1, None, x_rg)
+        flat = [g for lg in grads for g in lg]
+        return (dx0.sum(0) if x_rg else None, None, None, None, None, None, *flat)
+
+
+def mlp_forward(x2, layers, prior, S, sample=True, logprob=True, tf32=False):
+    flat = [t for layer in layers for t in layer]
+    return _MLPForward.apply(x2, prior, S, sample, logprob, tf32, *flat)
+
+
+class _FusedELBO(torch.autograd.Function):
+    """sample_elbo (networks.py:192-209) as 3 forward launches + likelihood + assembly; the
+    backward is 5 launches.  Only `loss` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, x2, target, beta, S, sigma, mode, prior, tf32, *flat):
+        L.require_cuda(x2, target, *flat)
+        x2 = _f32c(x2)
+        dev = x2.device
+        params = [tuple(_f32c(t) for t in flat[i:i + 4]) for i in range(0, len(flat), 4)]
+        eps = plan_eps([(tuple(p[0].shape), (p[0].shape[0],)) for p in params], S, dev, True)
+        acc = torch.zeros(2 * S + 1, dtype=torch.float64, device=dev)
+        logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
+        ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq)
+        out = ys[-1]
+        B, Cc = out.shape[1], out.shape[2]
+        need_grad = any(t.requires_grad for t in flat)
+        d_out = torch.empty_like(out) if need_grad else None
+        if mode == 'classification':
+            L.check(L.lib().bbb_nll_ce(L.ptr(out), L.ptr(target), S, B, Cc, 1.0 / S, L.ptr(nll), L.ptr(d_out),
+                                       L.stream()), 'bbb_nll_ce')
+        else:
+            tgt = _f32c(target)
+            L.check(L.lib().bbb_nll_gauss(L.ptr(out), L.ptr(tgt), float(sigma), S, B, Cc, 1.0 / S, L.ptr(nll),
+                                          L.ptr(d_out), L.stream()), 'bbb_nll_gauss')
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        L.check(L.lib().bbb_elbo_finalize(L.ptr(logp), L.ptr(logq), None, L.ptr(nll), S, float(beta), L.ptr(out4),
+                                          L.stream()), 'bbb_elbo_finalize')
+        if need_grad:
+            ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *eps.tensors())
+        ctx.cfg = (prior, S, float(beta), tf32, eps, len(params))
+        loss, lp, lq, nl = out4[0:1], out4[1], out4[2], out4[3:4]
+        ctx.mark_non_differentiable(lp, lq, nl)
+        return loss, lp, lq, nl
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        prior, S, beta, tf32, eps, nl = ctx.cfg
+        sv = ctx.saved_tensors
+        x2, d_out = sv[0], sv[1]
+        params = [tuple(_f32c(t) for t in sv[2 + 4 * i:6 + 4 * i]) for i in range(nl)]
+        ys = list(sv[2 + 4 * nl:2 + 4 * nl + nl - 1]) + [None]
+        scale = _f32c(g_loss).reshape(1)
+        _, grads = _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S,
+                                    None, None, 0, scale, False)
+        flat = [g for lg in grads for g in lg]
+        return (None,) * 8 + tuple(flat)
+
+
+def fused_elbo(x2, target, beta, S, sigma, mode, prior, layers, tf32=False):
+    flat = [t for layer in layers for t in layer]
+    return _FusedELBO.apply(x2, target, beta, S, sigma, mode, prior, tf32, *flat)
+
+
+# =========================================================================================
+# local reparameterisation
+# =========================================================================================
+def _lr_fwd(x, x_stride, p, eps, l, sigma_p, S, B, flags, y, delta, kl):
+    wm, wr, bm, br = p
+    inn, out = wm.shape
+    ea, eb = eps.ptrs(l)
+    rng = eps.rng(l)
+    L.check(L.lib().bbb_lr_linear_fwd(L.ptr(x), x_stride, L.ptr(wm), L.ptr(wr), L.ptr(bm), L.ptr(br), ea, eb,
+                                      C.byref(rng), sigma_p, S, B, inn, out, flags, L.ptr(y), L.ptr(delta),
+                                      L.ptr(kl), L.stream()), 'bbb_lr_linear_fwd')
+
+
+def _lr_bwd(dy, mask, x, x_stride, p, eps, l, delta, sigma_p, S, B, flags, g_kl, g_kl_dev, out_scale, dx, grads):
+    wm, wr, bm, br = p
+    inn, out = wm.shape
+    ea, eb = eps.ptrs(l)
+    rng = eps.rng(l)
+    L.check(L.lib().bbb_lr_linear_bwd(L.ptr(dy), L.ptr(mask), L.ptr(x), x_stride, L.ptr(wm), L.ptr(wr), L.ptr(bm),
+                                      L.ptr(br), ea, eb, C.byref(rng), L.ptr(delta), sigma_p, S, B, inn, out, flags,
+                                      g_kl, L.ptr(g_kl_dev), L.ptr(out_scale), L.ptr(dx), L.ptr(grads[0]),
+                                      L.ptr(grads[1]), L.ptr(grads[2]), L.ptr(grads[3]), L.stream()),
+            'bbb_lr_linear_bwd')
+
+
+def _net_lr_forward(x2, params, sigma_p, S, eps, sample, calc_kl, kl):
+    B = x2.shape[0]
+    ys, deltas = [], []
+    base = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if calc_kl else 0)
+    inp, stride = x2, 0
+    for l, p in enumerate(params):
+        inn, out = p[0].shape
+        y = torch.empty((S, B, out), dtype=torch.float32, device=x2.device)
+        d = torch.empty_like(y) if sample else None
+        _lr_fwd(inp, stride, p, eps, l, sigma_p, S, B, base | (L.F_RELU_IN if l > 0 else 0), y, d, kl)
+        ys.append(y)
+        deltas.append(d)
+        inp, stride = y, B * out
+    return ys, deltas
+
+
+def _net_lr_backward(x2, ys, deltas, d_out, params, sigma_p, S, eps, sample, calc_kl, g_kl, g_kl_dev, out_scale,
+                     need_dx0):
+    B = x2.shape[0]
+    base = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if calc_kl else 0)
+    grads = [None] * len(params)
+    dy, dx0 = d_out, None
+    for l in reversed(range(len(params))):
+        p = params[l]
+        inn, out = p[0].shape
+        g = tuple(torch.empty_like(t) for t in p)
+        flags = base | (L.F_RELU_IN if l > 0 else 0)
+        want_dx = l > 0 or need_dx0
+        dx = torch.empty((S, B, inn), dtype=torch.float32, device=x2.device) if want_dx else None
+        if not want_dx:
+            flags |= L.F_NO_DX
+        if l == 0 and need_dx0:
+            flags |= L.F_SCALE_DX
+        mask = ys[l] if l + 1 < len(params) else None
+        x_in, stride = (x2, 0) if l == 0 else (ys[l - 1], B * inn)
+        _lr_bwd(dy, mask, x_in, stride, p, eps, l, deltas[l], sigma_p, S, B, flags, g_kl, g_kl_dev, out_scale, dx, g)
+        grads[l] = g
+        dy = dx
+        if l == 0:
+            dx0 = dx
+    return dx0, grads
+
+
+class _LRLinear(torch.autograd.Function):
+    """BayesianLinearLR.forward for one sample (networks.py:116-138) -> (y, kl)."""
+
+    @staticmethod
+    def forward(ctx, x, wm, wr, bm, br, sigma_p, sample, calc_kl, layer_id):
+        L.require_cuda(x, wm, wr, bm, br)
+        inn, out = wm.shape
+        x2 = _f32c(x).reshape(-1, inn)
+        B = x2.shape[0]
+        p = tuple(_f32c(t) for t in (wm, wr, bm, br))
+        eps = plan_eps([((B, out), (out,))], 1, x2.device, sample)
+        if eps.injected is not None:
+            eps.injected = {layer_id: eps.injected[0]}
+        kl = torch.zeros(1, dtype=torch.float64, device=x2.device)
+        y = torch.empty((1, B, out), dtype=torch.float32, device=x2.device)
+        delta = torch.empty_like(y) if sample else None
+        flags = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if calc_kl else 0)
+        _lr_fwd(x2, 0, p, eps, layer_id, sigma_p, 1, B, flags, y, delta, kl)
+        saved = [x2, *p] + ([delta] if sample else []) + eps.tensors()
+        ctx.save_for_backward(*saved)
+        ctx.cfg = (sigma_p, sample, calc_kl, layer_id, eps, x.shape, x.requires_grad)
+        ctx.set_materialize_grads(False)
+        return y.view(*x.shape[:-1], out), kl.to(torch.float32)[0]
+
+    @staticmethod
+    def backward(ctx, dy, dkl):
+        sigma_p, sample, calc_kl, layer_id, eps, xshape, x_rg = ctx.cfg
+        sv = ctx.saved_tensors
+        x2, wm, wr, bm, br = sv[:5]
+        delta = sv[5] if sample else None
+        inn, out = wm.shape
+        B = x2.shape[0]
+        if dy is None:
+            dy = torch.zeros((B, out), dtype=torch.float32, device=x2.device)
+        dy = _f32c(dy).reshape(1, B, out)
+        g = tuple(torch.empty_like(t) for t in (wm, wr, bm, br))
+        dx = torch.empty((1, B, inn), dtype=torch.float32, device=x2.device) if x_rg else None
+        use_kl = calc_kl and dkl is not None
+        flags = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if use_kl else 0) | (0 if x_rg else L.F_NO_DX)
+        g_kl_dev = _f32c(dkl).reshape(1) if use_kl else None
+        _lr_bwd(dy, None, x2, 0, (wm, wr, bm, br), eps, layer_id, delta, sigma_p, 1, B, flags, 1.0, g_kl_dev, None,
+                dx, g)
+        return (dx.view(xshape) if x_rg else None, g[0], g[1], g[2], g[3], None, None, None, None)
+
+
+def lr_linear(x, wm, wr, bm, br, sigma_p, sample, calc_kl, layer_id=0):
+    return _LRLinear.apply(x, wm, wr, bm, br, float(sigma_p), sample, calc_kl, layer_id)
+
+
+def _lr_eps_shapes(params, B):
+    return [((B, p[0].shape[1]), (p[0].shape[1],)) for p in params]
+
+
+class _MLPForwardLR(torch.autograd.Function):
+    """S sampled forwards with LR layers -> outputs [S,B,C], kl [] (computed once, SURVEY B-8)."""
+
+    @staticmethod
+    def forward(ctx, x2, sigma_p, S, sample, calc_kl, *flat):
+        L.require_cuda(x2, *flat)
+        x2 = _f32c(x2)
+        params = [tuple(_f32c(t) for t in flat[i:i + 4]) for i in range(0, len(flat), 4)]
+        eps = plan_eps(_lr_eps_shapes(params, x2.shape[0]), S, x2.device, sample)
+        kl = torch.zeros(1, dtype=torch.float64, device=x2.device)
+        ys, deltas = _net_lr_forward(x2, params, sigma_p, S, eps, sample, calc_kl, kl)
+        ctx.save_for_backward(x2, *flat, *ys, *[d for d in deltas if d is not None], *eps.tensors())
+        ctx.cfg = (sigma_p, S, sample, calc_kl, eps, len(params), x2.requires_grad)
+        ctx.set_materialize_grads(False)
+        return ys[-1], kl.to(torch.float32)[0]
+
+    @staticmethod
+    def backward(ctx, d_out, dkl):
+        sigma_p, S, sample, calc_kl, eps, nl, x_rg = ctx.cfg
+        sv = ctx.saved_tensors
+        x2 = sv[0]
+        params = [tuple(_f32c(t) for t in sv[1 + 4 * i:5 + 4 * i]) for i in range(nl)]
+        ys = list(sv[1 + 4 * nl:1 + 5 * nl])
+        deltas = list(sv[1 + 5 * nl:1 + 6 * nl]) if sample else [None] * nl
+        if d_out is None:
+            d_out = torch.zeros_like(ys[-1])
+        use_kl = calc_kl and dkl is not None
+        g_kl_dev = _f32c(dkl).reshape(1) if use_kl else None
+        dx0, grads = _net_lr_backward(x2, ys, deltas, _f32c(d_out), params, sigma_p, S, eps, sample, use_kl, 1.0,
+                                      g_kl_dev, None, x_rg)
+        flat = [g for lg in grads for g in lg]
+        return (dx0.sum(0) if x_rg else None, None, None, None, None, *flat)
+
+
+def mlp_forward_lr(x2, layers, sigma_p, S, sample=True, calc_kl=True):
+    flat = [t for layer in layers for t in layer]
+    return _MLPForwardLR.apply(x2, float(sigma_p), S, sample, calc_kl, *flat)
+
+
+class _FusedELBOLR(torch.autograd.Function):
+    """sample_elbo_lr (networks.py:211-225): loss = beta * KL + NLL / S, KL evaluated once."""
+
+    @staticmethod
+    def forward(ctx, x2, target, beta, S, sigma, mode, sigma_p, *flat):
+        L.require_cuda(x2, target, *flat)
+        x2 = _f32c(x2)
+        dev = x2.device
+        params = [tuple(_f32c(t) for t in flat[i:i + 4]) for i in range(0, len(flat), 4)]
+        eps = plan_eps(_lr_eps_shapes(params, x2.shape[0]), S, dev, True)
+        acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        kl, nll = acc[0:1], acc[1:2]
+        ys, deltas = _net_lr_forward(x2, params, sigma_p, S, eps, True, True, kl)
+        out = ys[-1]
+        B, Cc = out.shape[1], out.shape[2]
+        need_grad = any(t.requires_grad for t in flat)
+        d_out = torch.empty_like(out) if need_grad else None
+        if mode == 'classification':
+            L.check(L.lib().bbb_nll_ce(L.ptr(out), L.ptr(target), S, B, Cc, 1.0 / S, L.ptr(nll), L.ptr(d_out),
+                                       L.stream()), 'bbb_nll_ce')
+        else:
+            tgt = _f32c(target)
+            L.check(L.lib().bbb_nll_gauss(L.ptr(out), L.ptr(tgt), float(sigma), S, B, Cc, 1.0 / S, L.ptr(nll),
+                                          L.ptr(d_out), L.stream()), 'bbb_nll_gauss')
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        L.check(L.lib().bbb_elbo_finalize(None, None, L.ptr(kl), L.ptr(nll), S, float(beta), L.ptr(out4),
+                                          L.stream()), 'bbb_elbo_finalize')
+        if need_grad:
+            ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *deltas, *eps.tensors())
+        ctx.cfg = (sigma_p, S, float(beta), eps, len(params))
+        loss, klm, nl = out4[0:1], out4[1], out4[2:3]
+        ctx.mark_non_differentiable(klm, nl)
+        return loss, klm, nl
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        sigma_p, S, beta, eps, nl = ctx.cfg
+        sv = ctx.saved_tensors
+        x2, d_out = sv[0], sv[1]
+        params = [tuple(_f32c(t) for t in sv[2 + 4 * i:6 + 4 * i]) for i in range(nl)]
+        o = 2 + 4 * nl
+        ys = list(sv[o:o + nl - 1]) + [None]
+        deltas = list(sv[o + nl - 1:o + 2 * nl - 1])
+        scale = _f32c(g_loss).reshape(1)
+        _, grads = _net_lr_backward(x2, ys, deltas, d_out, params, sigma_p, S, eps, True, True, beta, None, scale,
+                                    False)
+        flat = [g for lg in grads for g in lg]
+        return (None,) * 7 + tuple(flat)
+
+
+def fused_elbo_lr(x2, target, beta, S, sigma, mode, sigma_p, layers):
+    flat = [t for layer in layers for t in layer]
+    return _FusedELBOLR.apply(x2, target, beta, S, sigma, mode, float(sigma_p), *flat)
+
+
+# =========================================================================================
+# stand-alone reductions and the eps stream (tests, calculate_log_probs, diagnostics)
+# =========================================================================================
+def logprob_reduce(mu, rho, prior, eps=None, sample=True, seed=0, step=0, sample_idx=0, tensor_id=0,
+                   return_w=False):
+    L.require_cuda(mu, rho)
+    mu, rho = _f32c(mu), _f32c(rho)
+    n = mu.numel()
+    acc = torch.zeros(2, dtype=torch.float64, device=mu.device)
+    w = torch.empty_like(mu) if return_w else None
+    e = _f32c(eps) if eps is not None else None
+    L.check(L.lib().bbb_logprob_reduce(L.ptr(mu), L.ptr(rho), L.ptr(e), seed, step, sample_idx, tensor_id,
+                                       C.byref(prior), n, L.F_SAMPLE if sample else 0, L.ptr(w), L.ptr(acc[0:1]),
+                                       L.ptr(acc[1:2]), L.stream()), 'bbb_logprob_reduce')
+    return acc[0], acc[1], w
+
+
+def kl_gauss(mu, rho, sigma_p):
+    L.require_cuda(mu, rho)
+    mu, rho = _f32c(mu), _f32c(rho)
+    acc = torch.zeros(1, dtype=torch.float64, device=mu.device)
+    L.check(L.lib().bbb_kl_gauss(L.ptr(mu), L.ptr(rho), float(sigma_p), mu.numel(), L.ptr(acc), L.stream()),
+            'bbb_kl_gauss')
+    return acc[0]
+
+
+def philox_normal(n, device, seed=0, step=0, sample_idx=0, tensor_id=0):
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    L.require_cuda(out)
+    L.check(L.lib().bbb_philox_fill_normal(L.ptr(out), n, seed, step, sample_idx, tensor_id, L.stream()),
+            'bbb_philox_fill_normal')
+    return out

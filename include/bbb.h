@@ -1,0 +1,164 @@
+/*
+ * bbb.h -- C ABI of libbbb.so, the sm_100a Bayes-by-Backprop hot path.
+ *
+ * The reference (tennisonliu/bayesian-neural-network) has no FFI: its hot path is the
+ * Python module networks.py.  Each entry point below replaces the chain of eager ATen
+ * ops behind one reference function; the citation after "replaces" is the reference
+ * file:line.  The Python host (top-level networks.py + bayesian-neural-network_b200/)
+ * binds these with ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless said otherwise;
+ *    tensors are fp32, row-major, contiguous; sizes are int64_t; `stream` is a cudaStream_t.
+ *  - every function returns 0 on success, a negative BBB_E* code otherwise, never throws,
+ *    never synchronises; launch errors are read with cudaGetLastError right after the launch.
+ *    bbb_last_error_string() returns a thread-local message for the last failure.
+ *  - the library owns no device memory and keeps no state between calls.
+ *  - "S" is the number of Monte-Carlo samples handled by one call (one launch covers all).
+ *  - eps pointers are nullable.  Non-NULL: parity mode, eps is read from memory in the
+ *    reference's draw layout.  NULL: eps is generated in registers by Philox4x32-10 keyed by
+ *    (seed; element/4, sample_base + s, tensor id, step) and is never stored; the backward
+ *    call regenerates it from the same coordinates.
+ *  - double* accumulators are ADDED to (callers zero them once per step).
+ */
+#ifndef BBB_H_
+#define BBB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBB_VERSION 100
+
+/* error codes */
+#define BBB_OK 0
+#define BBB_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported flag)   */
+#define BBB_ECUDA (-2)    /* CUDA runtime / launch error, see bbb_last_error_string()        */
+#define BBB_EUNSUPPORTED (-3) /* shape not supported by the requested kernel family          */
+
+/* prior kinds: networks.py:61-68 */
+#define BBB_PRIOR_GAUSSIAN 0 /* Normal(0, sigma1); pi, sigma2 ignored                         */
+#define BBB_PRIOR_MIXTURE 1  /* pi N(0,sigma1) + (1-pi) N(0,sigma2)                           */
+
+/* flags */
+#define BBB_F_SAMPLE 1     /* w = mu + softplus(rho) eps; otherwise w = mu (networks.py:74-79) */
+#define BBB_F_LOGPROB 2    /* accumulate log prior / log posterior (or KL) (networks.py:81-83) */
+#define BBB_F_RELU_IN 4    /* the input x is a pre-activation: apply max(x,0) while loading    */
+#define BBB_F_ACCUM 8      /* backward: add into the grad buffers instead of overwriting       */
+#define BBB_F_TF32 16      /* allow the tcgen05 kind::tf32 tensor path when the shape supports it */
+#define BBB_F_NO_DX 32     /* backward: do not compute dx                                      */
+#define BBB_F_SCALE_DX 64  /* backward: out_scale_dev also multiplies dx                       */
+
+/* Philox tensor ids: weight tensor of layer l -> 2l, bias -> 2l+1, LR activation noise -> 2l */
+typedef struct bbb_rng {
+  uint64_t seed;        /* Philox key                                                          */
+  uint32_t step;        /* counter word 3: training step / call index                          */
+  uint32_t sample_base; /* counter word 1 = sample_base + s : global MC-sample index           */
+  uint32_t layer;       /* counter word 2 = 2*layer (+1 for the bias)                          */
+  const uint32_t *step_dev; /* optional DEVICE counter added to `step` when the kernel starts, so a
+                               CUDA graph that replays the launch still advances the eps stream    */
+} bbb_rng;
+
+typedef struct bbb_prior {
+  int32_t kind;
+  float pi, sigma1, sigma2;
+} bbb_prior;
+
+int bbb_version(void);
+const char *bbb_last_error_string(void);
+
+/* ---- weight-sampling layer ------------------------------------------------------------
+ * replaces BayesianLinear.forward (networks.py:73-88) = GaussianNode.sample (41-43) for W and b,
+ * ScaleMixtureGaussian.log_prob (24-27) / Normal.log_prob (67-68,82), GaussianNode.log_prob (45-46)
+ * and F.linear (88), for S samples at once.
+ *   x      [Sx,B,in]   x_sample_stride = B*in, or 0 when all samples share one input
+ *   w_mu,w_rho [out,in]; b_mu,b_rho [out]; eps_w [S,out,in] / eps_b [S,out] or NULL
+ *   y      [S,B,out]   written
+ *   logp, logq [S]     += sum log prior / sum log posterior over W and b (BBB_F_LOGPROB)
+ */
+int bbb_linear_fwd(const float *x, int64_t x_sample_stride, const float *w_mu, const float *w_rho,
+                   const float *b_mu, const float *b_rho, const float *eps_w, const float *eps_b,
+                   const bbb_rng *rng, const bbb_prior *prior, int64_t S, int64_t B, int64_t in,
+                   int64_t out, int32_t flags, float *y, double *logp, double *logq, void *stream);
+
+/* replaces the autograd backward of the above (triggered at reg_task.py:72, class_task.py:78,
+ * bandits.py:49).  With t = dy^T x - gp w R(w):  grad_mu = sum_s t,  grad_rho = sum_s
+ * sigmoid(rho) (t eps - gq / sigma)  (gp, gq = d loss / d logp_s, d logq_s).
+ *   dy        [S,B,out]  gradient w.r.t. y;  if dy_mask_src != NULL the effective gradient is
+ *                        dy * (dy_mask_src > 0)  (ReLU of this layer's output fused here)
+ *   gp, gq    host scalars;  gp_dev/gq_dev optional device multipliers read as gp_dev[s*g_dev_stride]
+ *             (stride 0: one value for all samples, 1: per sample) -- autograd hands these over as
+ *             device tensors and reading them on the device avoids a host synchronisation
+ *   out_scale_dev optional device scalar multiplying every parameter gradient written (d loss upstream)
+ *   dx        [S,B,in] written unless BBB_F_NO_DX (gradient w.r.t. the post-ReLU input)
+ *   grad_*    same shapes as the parameters; overwritten, or added to with BBB_F_ACCUM
+ */
+int bbb_linear_bwd(const float *dy, const float *dy_mask_src, const float *x, int64_t x_sample_stride,
+                   const float *w_mu, const float *w_rho, const float *b_mu, const float *b_rho,
+                   const float *eps_w, const float *eps_b, const bbb_rng *rng, const bbb_prior *prior,
+                   int64_t S, int64_t B, int64_t in, int64_t out, int32_t flags, float gp, float gq,
+                   const float *gp_dev, const float *gq_dev, int64_t g_dev_stride,
+                   const float *out_scale_dev, float *dx, float *grad_w_mu, float *grad_w_rho,
+                   float *grad_b_mu, float *grad_b_rho, void *stream);
+
+/* ---- local-reparameterisation layer ----------------------------------------------------
+ * replaces BayesianLinearLR.forward (networks.py:116-138) and compute_kl_cost (109-114).
+ *   w_mu,w_rho [in,out] (the reference's LR layout, networks.py:95-96)
+ *   eps_a [S,B,out] / eps_b [S,out] or NULL (Philox)
+ *   y [S,B,out] written;  delta [S,B,out] = sqrt(x^2 sigma^2) written when non-NULL (backward needs it)
+ *   kl  += closed-form KL(q || N(0,sigma_p)) of W and b, ONCE per call (it is sample-independent)
+ */
+int bbb_lr_linear_fwd(const float *x, int64_t x_sample_stride, const float *w_mu, const float *w_rho,
+                      const float *b_mu, const float *b_rho, const float *eps_a, const float *eps_b,
+                      const bbb_rng *rng, float sigma_p, int64_t S, int64_t B, int64_t in, int64_t out,
+                      int32_t flags, float *y, float *delta, double *kl, void *stream);
+
+/* backward of the above.  g_kl = d loss / d kl (host scalar), times
+ * g_kl_dev[0] when non-NULL; out_scale_dev as in bbb_linear_bwd. */
+int bbb_lr_linear_bwd(const float *dy, const float *dy_mask_src, const float *x, int64_t x_sample_stride,
+                      const float *w_mu, const float *w_rho, const float *b_mu, const float *b_rho,
+                      const float *eps_a, const float *eps_b, const bbb_rng *rng, const float *delta,
+                      float sigma_p, int64_t S, int64_t B, int64_t in, int64_t out, int32_t flags,
+                      float g_kl, const float *g_kl_dev, const float *out_scale_dev, float *dx,
+                      float *grad_w_mu, float *grad_w_rho, float *grad_b_mu, float *grad_b_rho,
+                      void *stream);
+
+/* ---- stand-alone single-pass reductions -------------------------------------------------
+ * bbb_logprob_reduce: one pass over (mu, rho[, eps]) -> optional w = mu + sigma eps, sum log p(w),
+ * sum log q(w)  (networks.py:24-27, 41-46, 82-83).  tensor_id is the full Philox counter word 2.
+ * bbb_kl_gauss: closed-form KL(q || N(0, sigma_p)) (networks.py:109-114).
+ * bbb_philox_fill_normal: the eps stream itself, for the statistical tests.
+ */
+int bbb_logprob_reduce(const float *mu, const float *rho, const float *eps, uint64_t seed, uint32_t step,
+                       uint32_t sample, uint32_t tensor_id, const bbb_prior *prior, int64_t n,
+                       int32_t flags, float *w_out, double *logp, double *logq, void *stream);
+int bbb_kl_gauss(const float *mu, const float *rho, float sigma_p, int64_t n, double *kl, void *stream);
+int bbb_philox_fill_normal(float *out, int64_t n, uint64_t seed, uint32_t step, uint32_t sample,
+                           uint32_t tensor_id, void *stream);
+
+/* ---- likelihood terms (BayesianNetwork.get_nll, networks.py:183-190) --------------------
+ * nll += sum over (s, b) of the negative log likelihood; dout (nullable) = grad_scale * d nll / d out.
+ * bbb_nll_ce:    logits [S,B,C], target int64 [B]       (CrossEntropyLoss(reduction='sum'))
+ * bbb_nll_gauss: out [S,B,D], target [B,D]              (-Normal(out, sigma).log_prob(target).sum())
+ */
+int bbb_nll_ce(const float *logits, const int64_t *target, int64_t S, int64_t B, int64_t C,
+               float grad_scale, double *nll, float *dlogits, void *stream);
+int bbb_nll_gauss(const float *out, const float *target, float sigma, int64_t S, int64_t B, int64_t D,
+                  float grad_scale, double *nll, float *dout, void *stream);
+
+/* ELBO assembly (networks.py:205-209 / 221-225):
+ * out4 = { beta mean(logq) - beta mean(logp) + nll/S, mean(logp), mean(logq), nll/S }   (kl == NULL)
+ * out4 = { beta kl + nll/S, kl, nll/S, 0 }                                              (kl != NULL)
+ */
+int bbb_elbo_finalize(const double *logp, const double *logq, const double *kl, const double *nll,
+                      int64_t S, float beta, float *out4, void *stream);
+
+/* *counter += inc  (advances a bbb_rng.step_dev between steps; one tiny launch, graph-capturable) */
+int bbb_counter_add(uint32_t *counter, uint32_t inc, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBB_H_ */

@@ -1,0 +1,121 @@
+"""Parity checks shared by the CPU host-logic suite (fake C ABI, device='cpu') and the GPU suite
+(real libbbb.so, device='cuda').  Each check drives the PUBLIC API the reference's callers use --
+BayesianNetwork / BayesianLinear[LR] from the drop-in `networks` module -- in the deterministic
+'reference' eps mode and compares with the fixtures recorded from the reference."""
+import numpy as np
+import torch
+
+import bnn_b200
+import networks
+from tests.golden_util import PNAMES
+
+# fp32 bound of BASELINE.json north_star: <= 1e-5 relative (max-norm per tensor for gradients, plus the
+# reference's own cancellation round-off, golden_util.Case.cancel_floor)
+RTOL = 1e-5
+
+
+def build_net(case, device, **extra):
+    mp = case.model_params()
+    mp.update(extra)
+    net = networks.BayesianNetwork(mp)
+    with torch.no_grad():
+        for li, layer in enumerate(net.layers()):
+            for pn, p in zip(PNAMES, case.layers[li]):
+                getattr(layer, pn).copy_(p)
+    return net.to(device)
+
+
+def net_grads(net):
+    return [[getattr(l, pn).grad.detach().cpu().numpy() for pn in PNAMES] for l in net.layers()]
+
+
+def check_train_step(case, device, fused=True, rtol=RTOL, **extra):
+    """zero_grad + sample_elbo[_lr] + backward through the network-level path."""
+    net = build_net(case, device, fused=fused, **extra)
+    net.train()
+    net.zero_grad()
+    x, y = case.x.to(device), case.y.to(device)
+    with bnn_b200.eps_mode('reference'):
+        torch.manual_seed(case.meta['seeds'][2])
+        if case.lr:
+            info = net.sample_elbo_lr(x, y, case.beta, case.S, sigma=case.sigma)
+        else:
+            info = net.sample_elbo(x, y, case.beta, case.S, sigma=case.sigma)
+    assert len(info) == (3 if case.lr else 4)
+    assert tuple(info[0].shape) == (1,) and info[1].dim() == 0 and tuple(info[-1].shape) == (1,)
+    info[0].backward()
+    case.check_scalar('loss', info[0].detach().cpu(), rtol)
+    if case.lr:
+        case.check_scalar('kl', info[1].detach().cpu(), rtol)
+        case.check_scalar('nll', info[2].detach().cpu(), rtol * 10)
+    else:
+        case.check_scalar('log_prior', info[1].detach().cpu(), rtol)
+        case.check_scalar('log_post', info[2].detach().cpu(), rtol)
+        case.check_scalar('nll', info[3].detach().cpu(), rtol * 10)
+    return case.check_grads(net_grads(net), rtol, allow_cancel_floor=True)
+
+
+def check_layerwise_train_step(case, device, rtol=RTOL):
+    """The reference's own loop (networks.py:199-208) written against the LAYER-level API:
+    net(x, sample=True) per sample, net.log_prior() / log_variational_posterior() / kl_cost()."""
+    net = build_net(case, device)
+    net.train()
+    net.zero_grad()
+    x, y = case.x.to(device), case.y.to(device)
+    S = case.S
+    outs = []
+    with bnn_b200.eps_mode('reference'):
+        torch.manual_seed(case.meta['seeds'][2])
+        a = torch.zeros(S, device=device)
+        b = torch.zeros(S, device=device)
+        nll = torch.zeros(1, device=device)
+        for i in range(S):
+            out = net(x, sample=True)
+            outs.append(out.detach().cpu().numpy())
+            if case.lr:
+                a[i] = net.kl_cost()
+            else:
+                a[i] = net.log_prior()
+                b[i] = net.log_variational_posterior()
+            nll = nll + net.get_nll(out, y, case.sigma)
+    if case.lr:
+        loss = case.beta * a.mean() + nll / S
+    else:
+        loss = case.beta * b.mean() - case.beta * a.mean() + nll / S
+    loss.backward()
+    case.check_scalar('loss', loss.detach().cpu(), rtol)
+    case.check_outputs(np.stack(outs), rtol)
+    return case.check_grads(net_grads(net), rtol, allow_cancel_floor=True)
+
+
+def check_eval_modes(case, device):
+    """networks.py:74-86: eval -> mean weights and int-0 log-probs; sample=True in eval draws weights
+    but skips the log-prob branch; calculate_log_probs=True evaluates them at w = mu."""
+    net = build_net(case, device)
+    net.eval()
+    x = case.x.to(device)
+    with torch.no_grad(), bnn_b200.eps_mode('reference'):
+        if not case.lr:
+            out = net(x)
+            np.testing.assert_allclose(out.cpu().numpy(), case.z['eval_mean_out'], rtol=1e-5, atol=1e-6)
+            assert net.l1.log_prior == 0 and isinstance(net.l1.log_prior, int)
+            assert net.log_prior() == 0
+        torch.manual_seed(case.meta['seeds'][2] + 1)
+        out = net(x, sample=True)
+        np.testing.assert_allclose(out.cpu().numpy(), case.z['eval_sampled_out'], rtol=1e-5, atol=2e-6)
+        if not case.lr:
+            h = x.view(-1, case.dims[0])
+            net.l1(h, False, True)
+            got = [float(net.l1.log_prior), float(net.l1.log_variational_posterior)]
+            np.testing.assert_allclose(got, case.z['l1_eval_logp'], rtol=2e-6)
+
+
+def check_state_dict(case, device):
+    """State-dict keys/shapes the reference's load_model_utils.py / weight_pruning.py rely on."""
+    net = build_net(case, device)
+    keys = list(net.state_dict().keys())
+    assert keys == [f'l{i}.{pn}' for i in (1, 2, 3) for pn in PNAMES]
+    d = case.dims
+    want = (d[0], d[1]) if case.lr else (d[1], d[0])
+    assert tuple(net.l1.weight_mu.shape) == want
+    assert all(('mu' in n) or ('rho' in n) for n, _ in net.named_parameters())

@@ -1,0 +1,96 @@
+"""CPU tests of the Python host (nn.Module mirror + autograd glue) against the golden fixtures, with
+the C ABI replaced by the test double in tests/fake_bbb.py.  No GPU, no product CPU path: the double
+is test infrastructure.  The same checks run against the real library in tests/test_gpu_parity.py."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import bnn_b200
+from tests import fake_bbb, parity_cases as PC
+from tests.golden_util import Case, SMALL, SMALL_LR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    return fake_bbb.install(monkeypatch)
+
+
+@pytest.mark.parametrize('name', SMALL + SMALL_LR + ['cfg4_bandit'])
+@pytest.mark.parametrize('fused', [True, False])
+def test_train_step_network_level(fake, name, fused):
+    PC.check_train_step(Case(name), 'cpu', fused=fused)
+    fused_used = ('nll_ce' in fake.calls) or ('nll_gauss' in fake.calls)
+    case = Case(name)
+    expect_fused = fused and not case.meta.get('flat_target', False)
+    assert fused_used == expect_fused        # [B] vs [B,1] broadcast targets (SURVEY B-3) take the general path
+
+
+@pytest.mark.parametrize('name', SMALL + SMALL_LR)
+def test_train_step_layer_level(fake, name):
+    PC.check_layerwise_train_step(Case(name), 'cpu')
+
+
+@pytest.mark.parametrize('name', SMALL + SMALL_LR)
+def test_eval_modes(fake, name):
+    PC.check_eval_modes(Case(name), 'cpu')
+
+
+@pytest.mark.parametrize('name', ['small_cls_mix', 'small_lr_cls'])
+def test_state_dict_layout(fake, name):
+    PC.check_state_dict(Case(name), 'cpu')
+
+
+def test_wrong_estimator_asserts(fake):
+    c, clr = Case('small_cls_mix'), Case('small_lr_cls')
+    with pytest.raises(AssertionError):
+        PC.build_net(c, 'cpu').sample_elbo_lr(c.x, c.y, 0.5, 1)
+    with pytest.raises(AssertionError):
+        PC.build_net(clr, 'cpu').sample_elbo(clr.x, clr.y, 0.5, 1)
+
+
+def test_local_reparam_defaults_to_false(fake):
+    """bandits.py:24-34 omits 'local_reparam'; the reference raises KeyError."""
+    mp = Case('small_bandit_bcast').model_params()
+    del mp['local_reparam']
+    net = bnn_b200.BayesianNetwork(mp)
+    assert net.local_reparam is False and isinstance(net.l1, bnn_b200.BayesianLinear)
+
+
+def test_deeper_network_extension(fake):
+    mp = Case('small_cls_mix').model_params()
+    mp['hidden_units'] = [12, 8, 8, 6]
+    net = bnn_b200.BayesianNetwork(mp)
+    assert net.n_layers == 5 and hasattr(net, 'l5') and hasattr(net, 'l4_act') and not hasattr(net, 'l5_act')
+
+
+def test_no_cpu_fallback():
+    """Without the double, CPU tensors are refused loudly (the CUDA path is the only path)."""
+    c = Case('small_cls_mix')
+    net = PC.build_net(c, 'cpu')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        net(c.x, sample=True)
+
+
+def test_library_exports_every_declared_symbol():
+    """libbbb.so loads and exports every function include/bbb.h declares (no compute calls)."""
+    hdr = open(os.path.join(ROOT, 'include', 'bbb.h')).read()
+    declared = set(re.findall(r'\b(bbb_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(bnn_b200._lib.EXPORTS), declared ^ set(bnn_b200._lib.EXPORTS)
+    lib = ctypes.CDLL(bnn_b200._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert bnn_b200._lib.lib().bbb_version() == 100
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'bayesian-neural-network_b200')
+    for fn in os.listdir(pkg) + ['../networks.py', '../config.py', '../bnn_b200.py']:
+        p = os.path.join(pkg, fn)
+        if p.endswith('.py'):
+            src = open(p).read()
+            assert 'import oracle' not in src and 'from oracle' not in src, fn
