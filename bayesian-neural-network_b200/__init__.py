@@ -2,11 +2,11 @@
 as hand-written sm_100a CUDA kernels (csrc/, C ABI in include/bbb.h) behind the reference's own
 networks.py API.  Import it as `bnn_b200` (bnn_b200.py at the repo root aliases this directory, whose
 name is not a Python identifier) or through the drop-in top-level `networks` module."""
-from . import _lib, rng, functional
+from . import _lib, rng, functional, parallel
 from .rng import set_eps_mode, get_eps_mode, manual_seed, eps_mode, set_sample_base, use_device_step
 from .layers import ScaleMixtureGaussian, GaussianNode, BayesianLinear, BayesianLinearLR
 from .network import BayesianNetwork, MLP, MLP_Dropout
 
 __all__ = ['ScaleMixtureGaussian', 'GaussianNode', 'BayesianLinear', 'BayesianLinearLR', 'BayesianNetwork',
            'MLP', 'MLP_Dropout', 'set_eps_mode', 'get_eps_mode', 'manual_seed', 'eps_mode', 'set_sample_base',
-           'use_device_step', 'functional', 'rng']
+           'use_device_step', 'functional', 'rng', 'parallel']

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbbb.so')
 
 # flags (include/bbb.h)
-F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX = 1, 2, 4, 8, 16, 32, 64
+F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
 PRIOR_GAUSSIAN, PRIOR_MIXTURE = 0, 1
 
 
@@ -26,6 +26,7 @@ P, I64, I32, F32, U32, U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_ui
 _SIGS = {
     'bbb_version': ([], C.c_int),
     'bbb_last_error_string': ([], C.c_char_p),
+    'bbb_launch_count': ([], C.c_uint64),
     'bbb_linear_fwd': ([P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, P, P, P, P], C.c_int),
     'bbb_linear_bwd': ([P, P, P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, F32, F32, P, P, I64, P,
                         P, P, P, P, P, P], C.c_int),

@@ -50,7 +50,8 @@ extern "C" int bbb_linear_bwd(const float *dy, const float *dy_mask_src, const f
                               const float *out_scale_dev, float *dx, float *grad_w_mu, float *grad_w_rho,
                               float *grad_b_mu, float *grad_b_rho, void *stream) {
   BBB_CHECK_ARG(dy && x && w_mu && w_rho && b_mu && b_rho, "null pointer");
-  BBB_CHECK_ARG(grad_w_mu && grad_w_rho && grad_b_mu && grad_b_rho, "null gradient pointer");
+  BBB_CHECK_ARG((flags & BBB_F_NO_WGRAD) || (grad_w_mu && grad_w_rho && grad_b_mu && grad_b_rho),
+                "null gradient pointer");
   BBB_CHECK_ARG((flags & BBB_F_NO_DX) || dx, "dx required unless BBB_F_NO_DX");
   BBB_CHECK_ARG(S >= 0 && B >= 0 && in >= 0 && out >= 0 && S <= 65535, "bad shape");
   BBB_CHECK_ARG(x_sample_stride == 0 || x_sample_stride == B * in, "x_sample_stride must be 0 or B*in");
@@ -109,7 +110,8 @@ extern "C" int bbb_lr_linear_bwd(const float *dy, const float *dy_mask_src, cons
                                  float *grad_w_mu, float *grad_w_rho, float *grad_b_mu, float *grad_b_rho,
                                  void *stream) {
   BBB_CHECK_ARG(dy && x && w_mu && w_rho && b_mu && b_rho, "null pointer");
-  BBB_CHECK_ARG(grad_w_mu && grad_w_rho && grad_b_mu && grad_b_rho, "null gradient pointer");
+  BBB_CHECK_ARG((flags & BBB_F_NO_WGRAD) || (grad_w_mu && grad_w_rho && grad_b_mu && grad_b_rho),
+                "null gradient pointer");
   BBB_CHECK_ARG((flags & BBB_F_NO_DX) || dx, "dx required unless BBB_F_NO_DX");
   BBB_CHECK_ARG(S >= 0 && B >= 0 && in >= 0 && out >= 0 && S <= 65535 && sigma_p > 0, "bad shape or sigma_p");
   BBB_CHECK_ARG(x_sample_stride == 0 || x_sample_stride == B * in, "x_sample_stride must be 0 or B*in");

@@ -14,6 +14,7 @@ namespace bbb {
 // ---------------------------------------------------------------------------------------
 char *last_error_buf();
 int fail(int code, const char *fmt, ...);
+void note_launch(int n = 1);  // diagnostic launch counter (bbb_launch_count)
 #define BBB_CHECK_ARG(cond, msg)                                         \
   do {                                                                   \
     if (!(cond)) return ::bbb::fail(BBB_EINVAL, "%s: %s", __func__, msg); \
@@ -22,6 +23,7 @@ int fail(int code, const char *fmt, ...);
   do {                                                                                            \
     cudaError_t e__ = cudaGetLastError();                                                         \
     if (e__ != cudaSuccess) return ::bbb::fail(BBB_ECUDA, "%s: %s", __func__, cudaGetErrorString(e__)); \
+    ::bbb::note_launch();                                                                         \
   } while (0)
 #define BBB_CHECK_CUDA(expr)                                                                      \
   do {                                                                                            \

@@ -379,6 +379,7 @@ int launch_lr_bwd_fma(const LrArgs &a, cudaStream_t st) {
     lr_dgrad_kernel<<<grid, NT, 0, st>>>(a);
     BBB_CHECK_LAUNCH();
   }
+  if (a.flags & BBB_F_NO_WGRAD) return BBB_OK;
   dim3 grid(cdiv(a.out, TN), cdiv(a.in, TM));
   lr_wgrad_kernel<<<grid, NT, 0, st>>>(a);
   BBB_CHECK_LAUNCH();

@@ -6,6 +6,8 @@
 // vectors, four independent vectors in flight per thread, grid = a multiple of the 148 SMs.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "bbb_common.cuh"
 
 namespace bbb {
@@ -22,6 +24,9 @@ int fail(int code, const char *fmt, ...) {
   va_end(ap);
   return code;
 }
+
+static std::atomic<uint64_t> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 namespace {
 
@@ -55,7 +60,7 @@ __global__ void __launch_bounds__(RT) logprob_reduce_kernel(const float *__restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float sg = softplus_f(r[j]);
-      w[j] = fmaf(sg, e[j], m[j]);
+      w[j] = __fadd_rn(m[j], __fmul_rn(sg, e[j]));
       lp += logp_elem(prior, w[j]);
       lq += logq_elem(sg, e[j]);
     }
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(RT) logprob_reduce_kernel(const float *__restr
     const float sg = softplus_f(rho[i]);
     float e = 0.0f;
     if (sample_flag) e = kInjected ? eps[i] : philox_normal1(rng, tensor, sample, (uint64_t)i);
-    const float w = fmaf(sg, e, mu[i]);
+    const float w = __fadd_rn(mu[i], __fmul_rn(sg, e));
     lp += logp_elem(prior, w);
     lq += logq_elem(sg, e);
     if (kWriteW) w_out[i] = w;
@@ -272,5 +277,6 @@ extern "C" int bbb_counter_add(uint32_t *counter, uint32_t inc, void *stream) {
   return BBB_OK;
 }
 
+extern "C" uint64_t bbb_launch_count(void) { return bbb::g_launches.load(std::memory_order_relaxed); }
 extern "C" int bbb_version(void) { return BBB_VERSION; }
 extern "C" const char *bbb_last_error_string(void) { return last_error_buf(); }

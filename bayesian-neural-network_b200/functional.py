@@ -37,6 +37,21 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+def _alloc_grads(params):
+    """Gradient buffers for every layer as consecutive views of ONE flat tensor, in parameter order, so a
+    multi-GPU step can all-reduce them with a single collective and no copies (parallel.py)."""
+    total = sum(t.numel() for p in params for t in p)
+    flat = torch.empty(total, dtype=torch.float32, device=params[0][0].device)
+    out, off = [], 0
+    for p in params:
+        g = []
+        for t in p:
+            g.append(flat[off:off + t.numel()].view(t.shape))
+            off += t.numel()
+        out.append(tuple(g))
+    return out
+
+
 class _EpsPlan:
     """eps for one call: injected tensors (reference mode) or Philox coordinates."""
 
@@ -60,12 +75,13 @@ def plan_eps(shapes, S, device, sample=True):
     draws follow SURVEY App. A-4: for s: for layer: weight eps, bias eps."""
     if not sample:
         return _EpsPlan()
-    if R.get_eps_mode() == 'reference':
+    if R.get_eps_mode() in ('reference', 'injected'):
+        draw = torch.randn if R.get_eps_mode() == 'reference' else R.pop_injected
         per = [([], []) for _ in shapes]
         for _ in range(S):
             for l, (sw, sb) in enumerate(shapes):
-                per[l][0].append(torch.randn(sw))
-                per[l][1].append(torch.randn(sb))
+                per[l][0].append(draw(sw))
+                per[l][1].append(draw(sb))
         inj = {l: (torch.stack(a).to(device), torch.stack(b).to(device)) for l, (a, b) in enumerate(per)}
         return _EpsPlan(inj)
     seed, step = R.next_step()
@@ -118,12 +134,12 @@ def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq,
     """Backward of _net_ws_forward.  Returns (dx0 or None, [grads per layer])."""
     B = x2.shape[0]
     base = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0)
-    grads = [None] * len(params)
+    grads = _alloc_grads(params)
     dy, dx0 = d_out, None
     for l in reversed(range(len(params))):
         p = params[l]
         out, inn = p[0].shape
-        g = tuple(torch.empty_like(t) for t in p)
+        g = grads[l]
         flags = base | (L.F_RELU_IN if l > 0 else 0)
         want_dx = l > 0 or need_dx0
         dx = torch.empty((S, B, inn), dtype=torch.float32, device=x2.device) if want_dx else None
@@ -135,7 +151,6 @@ def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq,
         x_in, stride = (x2, 0) if l == 0 else (ys[l - 1], B * inn)
         _ws_bwd(dy, mask, x_in, stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev, gq_dev, g_stride, out_scale,
                 dx, g)
-        grads[l] = g
         dy = dx
         if l == 0:
             dx0 = dx
@@ -335,12 +350,12 @@ def _net_lr_backward(x2, ys, deltas, d_out, params, sigma_p, S, eps, sample, cal
                      need_dx0):
     B = x2.shape[0]
     base = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if calc_kl else 0)
-    grads = [None] * len(params)
+    grads = _alloc_grads(params)
     dy, dx0 = d_out, None
     for l in reversed(range(len(params))):
         p = params[l]
         inn, out = p[0].shape
-        g = tuple(torch.empty_like(t) for t in p)
+        g = grads[l]
         flags = base | (L.F_RELU_IN if l > 0 else 0)
         want_dx = l > 0 or need_dx0
         dx = torch.empty((S, B, inn), dtype=torch.float32, device=x2.device) if want_dx else None
@@ -351,7 +366,6 @@ def _net_lr_backward(x2, ys, deltas, d_out, params, sigma_p, S, eps, sample, cal
         mask = ys[l] if l + 1 < len(params) else None
         x_in, stride = (x2, 0) if l == 0 else (ys[l - 1], B * inn)
         _lr_bwd(dy, mask, x_in, stride, p, eps, l, deltas[l], sigma_p, S, B, flags, g_kl, g_kl_dev, out_scale, dx, g)
-        grads[l] = g
         dy = dx
         if l == 0:
             dx0 = dx

@@ -21,8 +21,19 @@ def _st():
 
 
 def set_eps_mode(mode):
-    assert mode in ('philox', 'reference')
+    assert mode in ('philox', 'reference', 'injected')
     _st().mode = mode
+
+
+def set_injected_eps(tensors):
+    """'injected' mode: a list of tensors consumed in the reference's draw order (tests)."""
+    _st().queue = list(tensors)
+
+
+def pop_injected(shape):
+    t = _st().queue.pop(0)
+    assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+    return t
 
 
 def get_eps_mode():

@@ -1,0 +1,471 @@
+#!/usr/bin/env python
+"""Benchmark of the Bayes-by-Backprop hot path (BASELINE.json metric: BBB ELBO train steps/s,
+batch x MC samples/s, % roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload mnist|wide|...]
+
+One step = what the reference's train_step does per minibatch (class_task.py:70-79):
+zero_grad + sample_elbo(x, y, beta, S) + loss.backward() + Adam.step().
+Default workload = BASELINE.json configs[1]: MNIST-shape 784-1200-1200-10, batch 128, S = 2, scale-mixture
+prior [0.5, 0, -8], synthetic inputs.  One JSON line is printed by rank 0 (see DESIGN.md "Measurement").
+
+--impl reference times the reference's CPU path for the same step on this box's host cores: the unmodified
+reference from baseline/_ref/ when __graft_entry__.build() staged it, else the oracle port (oracle/bbb_oracle.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: dims, B, S, mode, prior_init, mixture, M (num_batches for beta), lr, local_reparam
+    'mnist': dict(dims=[784, 1200, 1200, 10], B=128, S=2, mode='classification', prior_init=[0.5, -0, -8],
+                  mixture=True, M=468, lr=1e-4, lrp=False, img=(1, 28, 28)),
+    'mnist_lr': dict(dims=[784, 1200, 1200, 10], B=128, S=2, mode='classification', prior_init=[1.],
+                     mixture=False, M=468, lr=1e-4, lrp=True, img=(1, 28, 28)),
+    'regression': dict(dims=[1, 400, 400, 1], B=128, S=5, mode='regression', prior_init=[0.5, -0, -6],
+                       mixture=True, M=8, lr=1e-3, lrp=False, sigma=0.1),
+    'bandit': dict(dims=[119, 100, 100, 1], B=64, S=2, mode='regression', prior_init=[0.5, -0, -6],
+                   mixture=True, M=64, lr=1e-4, lrp=False),
+    'wide': dict(dims=[4096, 4096, 4096, 4096, 4096, 10], B=4096, S=64, mode='classification',
+                 prior_init=[0.5, -0, -6], mixture=True, M=2, lr=1e-4, lrp=False),
+}
+MU_INIT, RHO_INIT = [-0.2, 0.2], [-5, -4]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='mnist', choices=sorted(WORKLOADS))
+    ap.add_argument('--samples', type=int, default=0, help='override S (MC samples per step per job)')
+    ap.add_argument('--tf32', type=int, default=-1, help='1: tcgen05 kind::tf32 path, 0: exact fp32 FMA, -1: default')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-budget-s', type=float, default=25.0)
+    return ap.parse_args()
+
+
+def beta_of(w):
+    return 2 ** (w['M'] - 1) / (2 ** w['M'] - 1)
+
+
+def make_inputs(w, torch, B=None):
+    B = B or w['B']
+    g = torch.Generator().manual_seed(1)
+    d = w['dims']
+    if w['mode'] == 'classification':
+        shape = (B, *w['img']) if 'img' in w else (B, d[0])
+        x = torch.rand(*shape, generator=g) if 'img' in w else torch.randn(*shape, generator=g)
+        y = torch.randint(0, d[-1], (B,), generator=g)
+    else:
+        x = torch.randn(B, d[0], generator=g)
+        y = torch.randn(B, d[-1], generator=g)
+    return x, y
+
+
+def model_params(w):
+    d = w['dims']
+    return dict(input_shape=d[0], classes=d[-1], batch_size=w['B'], hidden_units=d[1:-1], mode=w['mode'],
+                mu_init=MU_INIT, rho_init=RHO_INIT, prior_init=w['prior_init'], mixture_prior=w['mixture'],
+                local_reparam=w['lrp'])
+
+
+def algorithmic(w, S):
+    """bytes/step = (16 S + 8) P + A, A = S 4 B (2 d_in + 4 sum(hidden) + 3 d_out);
+    GEMM flops/step = S (6 B P_w - 2 B P_w1)  (x2 for LR)."""
+    d, B = w['dims'], w['B']
+    Pw = sum(a * b for a, b in zip(d[:-1], d[1:]))
+    P = Pw + sum(d[1:])
+    A = S * 4 * B * (2 * d[0] + 4 * sum(d[1:-1]) + 3 * d[-1])
+    flops = S * (6 * B * Pw - 2 * B * d[0] * d[1]) * (2 if w['lrp'] else 1)
+    return dict(P=P, Pw=Pw, bytes=(16 * S + 8) * P + A, flops=flops)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU path (or the oracle port) on host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    os.environ['CUDA_VISIBLE_DEVICES'] = ''           # config.DEVICE must resolve to cpu
+    import torch
+    ncores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(ncores)
+    w = dict(WORKLOADS[args.workload])
+    S = args.samples or w['S']
+    x, y = make_inputs(w, torch)
+    beta = beta_of(w)
+    sigma = w.get('sigma', 1.0)
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    three_layer = len(w['dims']) == 4
+    if os.path.isfile(os.path.join(ref_dir, 'networks.py')) and three_layer:
+        kind = 'reference'
+        import importlib.util
+        import tempfile
+        os.chdir(tempfile.mkdtemp())                  # the reference writes ./runs and ./saved_models
+        for name in ('config', 'networks'):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(ref_dir, name + '.py'))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+        torch.manual_seed(0)
+        mp = model_params(w)
+        mp['hidden_units'] = w['dims'][1]
+        net = sys.modules['networks'].BayesianNetwork(mp)
+        net.train()
+        opt = torch.optim.Adam(net.parameters(), lr=w['lr'])
+
+        def step():
+            net.zero_grad()
+            fn = net.sample_elbo_lr if w['lrp'] else net.sample_elbo
+            loss = fn(x, y, beta, S, sigma=sigma)[0]
+            loss.backward()
+            opt.step()
+            return loss
+    else:
+        kind = 'port'
+        from oracle import bbb_oracle as O
+        torch.manual_seed(0)
+        layers = [tuple(p.requires_grad_(True) for p in layer)
+                  for layer in O.init_layers(w['dims'], MU_INIT, RHO_INIT, local_reparam=w['lrp'])]
+        prior = O.make_prior(w['prior_init'], w['mixture'])
+        opt = torch.optim.Adam([p for layer in layers for p in layer], lr=w['lr'])
+
+        def step():
+            eps = O.draw_eps(w['dims'], S, batch=w['B'], local_reparam=w['lrp'])
+            out = O.train_step(x, y, layers, prior[1] if w['lrp'] else prior, eps, beta, w['mode'], sigma,
+                               local_reparam=w['lrp'])
+            opt.step()
+            return out[0]
+
+    t0 = time.perf_counter()
+    step()
+    t_first = time.perf_counter() - t0
+    budget = args.cpu_budget_s if args.cpu_budget_s > 0 else 25.0
+    warm = max(0, min(args.warmup, int(0.2 * budget / max(t_first, 1e-6))))
+    for _ in range(warm):
+        step()
+    n = max(2, min(args.steps, int(budget / max(t_first, 1e-6))))
+    times = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    ms = 1e3 * times[len(times) // 2]
+    value = w['B'] * S / (ms * 1e-3)
+    line = dict(metric='bbb_elbo_train_throughput', value=value, unit='batch*MC samples/s', impl='reference',
+                n_gpus=args.gpus, steps=n, warmup=warm, ms_per_step=ms, steps_per_s=1e3 / ms,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload=workload_name(args.workload, w, S), optimizer='Adam (torch.optim)',
+                            device='cpu'),
+                cpu_baseline=dict(value=value, unit='batch*MC samples/s', cores=ncores, kind=kind,
+                                  sample=f'{n} full train steps of the same workload (median), {warm} warm-up, '
+                                         f'torch {torch.__version__} CPU, {ncores} threads'),
+                e2e=dict(value=value, unit='batch*MC samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(name, w, S):
+    return (f"{name}: BBB {'LR ' if w['lrp'] else ''}MLP {'-'.join(map(str, w['dims']))}, batch {w['B']}, "
+            f"S={S} MC samples/step/GPU, {'mixture' if w['mixture'] else 'gaussian'} prior {w['prior_init']}, "
+            f"{w['mode']}, synthetic inputs")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                       '-lms', '100', '-i', str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        for r in rows:
+            f = [c.strip() for c in r.split(',')]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class CallTimer:
+    """Proxy over the ctypes library that brackets every C-ABI call with CUDA events on the launching
+    (current torch) stream.  Backward calls are split into their two kernels (dgrad-only, wgrad-only) so every
+    timed interval is exactly one kernel.  Used outside the timed region only."""
+
+    def __init__(self, lib, torch, L):
+        self.lib, self.torch, self.L, self.records = lib, torch, L, []
+
+    def __getattr__(self, name):
+        fn = getattr(self.lib, name)
+        if not name.startswith('bbb_') or name in ('bbb_last_error_string', 'bbb_version', 'bbb_launch_count'):
+            return fn
+        torch, L = self.torch, self.L
+
+        def timed(tag, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a)
+            e1.record()
+            self.records.append((tag, e0, e1, a))
+            return r
+
+        def call(*a):
+            if name in ('bbb_linear_bwd', 'bbb_lr_linear_bwd'):
+                fi = 16 if name == 'bbb_linear_bwd' else 17
+                flags = a[fi]
+                r = 0
+                if not flags & L.F_NO_DX:
+                    b = list(a); b[fi] = flags | L.F_NO_WGRAD
+                    r |= timed(name + ':dgrad', *b)
+                b = list(a); b[fi] = flags | L.F_NO_DX
+                r |= timed(name + ':wgrad', *b)
+                return r
+            return timed(name, *a)
+        return call
+
+
+def kernel_bytes(tag, a, L):
+    """Algorithmic bytes of one launch: every operand the kernel must read or write once."""
+    if tag.startswith('bbb_linear_fwd') or tag.startswith('bbb_lr_linear_fwd'):
+        S, B, inn, out = a[10:14]
+        x_shared = a[1] == 0
+        return S * 8 * inn * out + 4 * B * inn * (1 if x_shared else S) + 4 * S * B * out * (2 if 'lr' in tag else 1)
+    if tag.startswith('bbb_linear_bwd') or tag.startswith('bbb_lr_linear_bwd'):
+        S, B, inn, out = a[12:16] if tag.startswith('bbb_linear_bwd') else a[13:17]
+        mask = 4 * S * B * out if a[1] else 0
+        x_shared = a[3] == 0
+        act = 4 * S * B * out + mask + 4 * B * inn * (1 if x_shared else S)
+        if tag.endswith(':dgrad'):
+            return S * 8 * inn * out + 4 * S * B * out + mask + 4 * S * B * inn
+        return S * 8 * inn * out + 8 * inn * out + act
+    return None
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import bnn_b200
+    from bnn_b200 import _lib as L
+    from bnn_b200 import parallel
+
+    w = dict(WORKLOADS[args.workload])
+    S = args.samples or w['S']                 # per-GPU MC samples (weak scaling over the sample axis)
+    tf32 = (args.tf32 == 1)
+    mp = model_params(w)
+    mp['tf32'] = tf32
+    torch.manual_seed(0)
+    net = bnn_b200.BayesianNetwork(mp).to(dev)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=w['lr'])
+    bnn_b200.manual_seed(2)
+    bnn_b200.set_sample_base(rank * S)          # disjoint Philox sample indices per rank
+    x_h, y_h = make_inputs(w, torch)
+    x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+    beta, sigma = beta_of(w), w.get('sigma', 1.0)
+    loss_h = torch.empty(1, pin_memory=True)
+    elbo = net.sample_elbo_lr if w['lrp'] else net.sample_elbo
+
+    def step(x, y):
+        net.zero_grad()
+        loss = elbo(x, y, beta, S, sigma=sigma)[0]
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_gradients(net, world)
+        opt.step()
+        return loss
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def timed_steps(n, e2e):
+        """n steps; each step bracketed by CUDA events, L2 flushed between steps outside the brackets."""
+        evs = []
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if e2e:
+                xd = x_h.to(dev, non_blocking=True)
+                yd = y_h.to(dev, non_blocking=True)
+                loss = step(xd, yd)
+                loss_h.copy_(loss.detach(), non_blocking=True)
+            else:
+                step(x_d, y_d)
+            e1.record()
+            if e2e:
+                e1.synchronize()                 # the caller reads the loss every step
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    timed_steps(max(3, args.warmup), False)
+    launches0 = L.lib().bbb_launch_count()
+    barrier()
+    clocks = Clocks(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    ms_list = timed_steps(args.steps, False)
+    barrier()
+    t1 = time.perf_counter()
+    clk = clocks.stop(t0, t1) if clocks else None
+    launches = (L.lib().bbb_launch_count() - launches0) // max(1, args.steps)
+    timed_steps(3, True)
+    barrier()
+    ms_e2e = timed_steps(args.steps, True)
+    barrier()
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    ms = reduce_max(sum(ms_list) / len(ms_list))
+    ms2 = reduce_max(sum(ms_e2e) / len(ms_e2e))
+
+    # ---- per-kernel timing (outside the timed region): which kernel dominates, and its roofline
+    roof, kern_table = None, None
+    if rank == 0:
+        real = L.lib()
+        prox = CallTimer(real, torch, L)
+        L._lib = prox
+        try:
+            for _ in range(3):
+                step(x_d, y_d)
+            prox.records.clear()
+            reps = 20
+            for _ in range(reps):
+                flush.zero_()
+                step(x_d, y_d)
+            torch.cuda.synchronize()
+        finally:
+            L._lib = real
+        agg = {}
+        for tag, e0, e1, a in prox.records:
+            key = tag
+            if 'linear' in tag:
+                inn, out = (a[12], a[13]) if 'fwd' in tag else ((a[14], a[15]) if tag.startswith('bbb_linear_bwd') else (a[15], a[16]))
+                key = f'{tag}[{inn}x{out}]'
+            d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=kernel_bytes(tag, a, L)))
+            d['ms'] += e0.elapsed_time(e1)
+            d['n'] += 1
+        tot = sum(d['ms'] for d in agg.values())
+        kern_table = {k: dict(us=1e3 * d['ms'] / d['n'], share=d['ms'] / tot, launches_per_step=d['n'] // reps)
+                      for k, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])}
+        top = next(k for k in kern_table if agg[k]['bytes'])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        us = kern_table[top]['us']
+        ach = agg[top]['bytes'] / (us * 1e-6) / 1e9
+        roof = dict(kernel=top, bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
+                    us_per_launch=us, share_of_step=kern_table[top]['share'],
+                    peak_source='MEASURED_PEAKS.json hbm_gbs (measured)' if peaks else 'fallback 6650 GB/s',
+                    algorithmic_bytes_per_launch=agg[top]['bytes'])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    alg = algorithmic(w, S)
+    value = world * w['B'] * S / (ms * 1e-3)
+    e2e_v = world * w['B'] * S / (ms2 * 1e-3)
+    peaks_hbm = roof['peak'] if roof else 6650.0
+    step_roof = dict(algorithmic_bytes_per_step=alg['bytes'], hbm_floor_us=alg['bytes'] / peaks_hbm / 1e3,
+                     frac_of_hbm_roofline=(alg['bytes'] / peaks_hbm / 1e3) / (ms * 1e3),
+                     gemm_flops_per_step=alg['flops'], achieved_tflops=alg['flops'] / (ms * 1e-3) / 1e12)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload',
+                                  args.workload, '--steps', '40', '--warmup', '1', '--cpu-budget-s',
+                                  str(args.cpu_budget_s)] + (['--samples', str(S)] if args.samples else []),
+                                 capture_output=True, text=True, timeout=600)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])['cpu_baseline']
+        except Exception as e:     # the baseline is reported, never required for the GPU number
+            cpu = dict(value=None, unit='batch*MC samples/s', cores=None, kind='port', sample=f'failed: {e}')
+    line = dict(metric='bbb_elbo_train_throughput', value=value, unit='batch*MC samples/s', n_gpus=world,
+                steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, steps_per_s=1e3 / ms,
+                higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='tf32' if tf32 else 'f32', data='synthetic',
+                config=dict(workload=workload_name(args.workload, w, S), optimizer='Adam (torch.optim, foreach)',
+                            parallelism=f'MC samples sharded over {world} GPU(s), disjoint Philox sample indices'
+                                        + (', NCCL all-reduce of the mu/rho gradients' if world > 1 else ''),
+                            l2='flushed between timed steps (256 MiB write), flush outside the CUDA-event brackets',
+                            eps='Philox4x32-10 in registers, regenerated in backward',
+                            gemm='tcgen05 kind::tf32' if tf32 else 'fp32 FMA (exact mode)'),
+                e2e=dict(value=e2e_v, unit='batch*MC samples/s', ms_per_step=ms2,
+                         h2d_bytes_per_step=x_h.numel() * 4 + y_h.numel() * y_h.element_size(),
+                         d2h_bytes_per_step=4),
+                gpu_launches=int(launches), clocks=clk, roofline=roof, step_roofline=step_roof,
+                kernels=kern_table, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        if int(os.environ.get('RANK', 0)) == 0:
+            run_reference(args)
+        return
+    run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

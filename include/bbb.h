@@ -50,6 +50,7 @@ extern "C" {
 #define BBB_F_TF32 16      /* allow the tcgen05 kind::tf32 tensor path when the shape supports it */
 #define BBB_F_NO_DX 32     /* backward: do not compute dx                                      */
 #define BBB_F_SCALE_DX 64  /* backward: out_scale_dev also multiplies dx                       */
+#define BBB_F_NO_WGRAD 128 /* backward: do not compute parameter gradients (dx only)           */
 
 /* Philox tensor ids: weight tensor of layer l -> 2l, bias -> 2l+1, LR activation noise -> 2l */
 typedef struct bbb_rng {
@@ -68,6 +69,8 @@ typedef struct bbb_prior {
 
 int bbb_version(void);
 const char *bbb_last_error_string(void);
+/* number of kernels this library has launched in this process (diagnostic; bench.py's gpu_launches) */
+uint64_t bbb_launch_count(void);
 
 /* ---- weight-sampling layer ------------------------------------------------------------
  * replaces BayesianLinear.forward (networks.py:73-88) = GaussianNode.sample (41-43) for W and b,

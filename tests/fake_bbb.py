@@ -13,7 +13,7 @@ import numpy as np
 
 from oracle import closed_form as CF
 
-F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX = 1, 2, 4, 8, 16, 32, 64
+F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 def _arr(ptr, ctype, *shape):
@@ -46,6 +46,9 @@ class FakeLib:
 
     def bbb_last_error_string(self):
         return b'fake'
+
+    def bbb_launch_count(self):
+        return len(self.calls)
 
     # ---------------------------------------------------------------- weight sampling
     def bbb_linear_fwd(self, x, xs, wm, wr, bm, br, ew, eb, rng, prior, S, B, inn, out, flags, y, logp, logq, st):

@@ -125,6 +125,21 @@ def test_philox_mode_equals_injecting_the_same_stream(name):
     g1 = PC.net_grads(net)
 
     eps = _philox_eps_for(c.dims, c.S, seed, step, lr_batch=c.B if c.lr else None)
+    # (a) bit-exact: the same stream injected through the parity path gives identical results
+    net2 = PC.build_net(c, DEV)
+    net2.train()
+    bnn_b200.rng.set_injected_eps([t for per in eps for pair in per for t in pair])
+    with bnn_b200.eps_mode('injected'):
+        info2 = net2.sample_elbo_lr(x, y, c.beta, c.S, c.sigma) if c.lr else net2.sample_elbo(x, y, c.beta, c.S, c.sigma)
+    info2[0].backward()
+    # (the loss goes through fp64 atomics whose order is not fixed: equal to fp32 round-off; gradients bit-exact)
+    assert abs(float(info2[0].detach()) - float(info[0].detach())) <= 1e-6 * abs(float(info[0].detach()))
+    for ga, gb in zip(PC.net_grads(net2), g1):
+        for a, b in zip(ga, gb):
+            assert np.array_equal(a, b)
+    # (b) against the float64 closed form.  With the e^-8 mixture component d(w R(w))/dw reaches 1/sigma2^2 =
+    # 8.9e6, so the fp32 rounding of w alone (6e-8 relative) moves the gradient by up to ~3e-5 of its max-norm:
+    # an fp32-vs-fp64 conditioning effect the reference shares; 5e-5 is the stated bound for this comparison.
     layers = [tuple(p.double().numpy() for p in layer) for layer in c.layers]
     eps_np = [[(a.double().cpu().numpy(), b.double().cpu().numpy()) for a, b in per] for per in eps]
     xx = c.x.double().numpy()
@@ -133,12 +148,12 @@ def test_philox_mode_equals_injecting_the_same_stream(name):
         r = CF.elbo_step_lr(xx, yy, layers, c.prior[1], eps_np, c.beta, c.mode, c.sigma)
     else:
         r = CF.elbo_step(xx, yy, layers, c.prior, eps_np, c.beta, c.mode, c.sigma)
-    assert abs(float(info[0]) - r['loss']) <= 1e-5 * abs(r['loss'])
+    assert abs(float(info[0].detach()) - r['loss']) <= 1e-5 * abs(r['loss'])
     for li in range(3):
         for pi in range(4):
             ref = r['grads'][li][pi]
             err = np.abs(g1[li][pi] - ref).max() / np.abs(ref).max()
-            assert err <= 1e-5, (name, li, PNAMES[pi], err)
+            assert err <= 5e-5, (name, li, PNAMES[pi], err)
 
 
 def test_philox_step_is_replayable_and_advances():
