@@ -29,8 +29,11 @@ def net_grads(net):
     return [[getattr(l, pn).grad.detach().cpu().numpy() for pn in PNAMES] for l in net.layers()]
 
 
-def check_train_step(case, device, fused=True, rtol=RTOL, **extra):
-    """zero_grad + sample_elbo[_lr] + backward through the network-level path."""
+def check_train_step(case, device, fused=True, rtol=RTOL, rtol_gemm=None, **extra):
+    """zero_grad + sample_elbo[_lr] + backward through the network-level path.
+    rtol bounds the log-prob / KL scalars; rtol_gemm (default rtol) bounds everything downstream of a GEMM
+    (NLL, loss, gradients) -- looser in the TF32 tensor-core mode."""
+    rg = rtol if rtol_gemm is None else rtol_gemm
     net = build_net(case, device, fused=fused, **extra)
     net.train()
     net.zero_grad()
@@ -44,15 +47,15 @@ def check_train_step(case, device, fused=True, rtol=RTOL, **extra):
     assert len(info) == (3 if case.lr else 4)
     assert tuple(info[0].shape) == (1,) and info[1].dim() == 0 and tuple(info[-1].shape) == (1,)
     info[0].backward()
-    case.check_scalar('loss', info[0].detach().cpu(), rtol)
+    case.check_scalar('loss', info[0].detach().cpu(), rg)
     if case.lr:
         case.check_scalar('kl', info[1].detach().cpu(), rtol)
-        case.check_scalar('nll', info[2].detach().cpu(), rtol * 10)
+        case.check_scalar('nll', info[2].detach().cpu(), rg * 10)
     else:
         case.check_scalar('log_prior', info[1].detach().cpu(), rtol)
         case.check_scalar('log_post', info[2].detach().cpu(), rtol)
-        case.check_scalar('nll', info[3].detach().cpu(), rtol * 10)
-    return case.check_grads(net_grads(net), rtol, allow_cancel_floor=True)
+        case.check_scalar('nll', info[3].detach().cpu(), rg * 10)
+    return case.check_grads(net_grads(net), rg, allow_cancel_floor=True)
 
 
 def check_layerwise_train_step(case, device, rtol=RTOL):
