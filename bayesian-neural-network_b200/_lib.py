@@ -38,7 +38,8 @@ _SIGS = {
     'bbb_philox_fill_normal': ([P, I64, U64, U32, U32, U32, P], C.c_int),
     'bbb_nll_ce': ([P, P, I64, I64, I64, F32, P, P, P], C.c_int),
     'bbb_nll_gauss': ([P, P, F32, I64, I64, I64, F32, P, P, P], C.c_int),
-    'bbb_elbo_finalize': ([P, P, P, P, I64, F32, P, P], C.c_int),
+    'bbb_elbo_finalize': ([P, P, P, P, I64, F32, P, P, P], C.c_int),
+    'bbb_adam_step': ([I32, P, P, P, P, P, F32, F32, F32, F32, U32, P, P, P], C.c_int),
     'bbb_counter_add': ([P, U32, P], C.c_int),
 }
 EXPORTS = tuple(_SIGS)

@@ -110,11 +110,15 @@ __device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1]
   return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
+// Box-Muller on the SFU: lg2 / sqrt / sin / cos approximations (abs error ~2^-21, far below the sampling
+// noise; moments and KS are checked in tests/test_gpu_parity.py).  ~12 instructions per pair.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &z0, float &z1) {
-  float u = u32_to_unit(a), v = u32_to_unit(b);
-  float r = sqrtf(-2.0f * logf(u));
+  const float u = u32_to_unit(a), v = u32_to_unit(b);
+  const float t = -2.0f * __logf(u);                 // >= 0
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
   float s, c;
-  sincospif(2.0f * v, &s, &c);
+  __sincosf(6.283185307179586f * v, &s, &c);         // argument in (0, 2 pi]
   z0 = r * s;
   z1 = r * c;
 }
@@ -177,6 +181,26 @@ __device__ __forceinline__ float prior_R(const PriorDev &p, float w) {
   float ea = expf(a - m), eb = expf(b - m);
   float inv = 1.0f / (ea + eb);
   return (ea * p.inv_var1 + eb * p.inv_var2) * inv;
+}
+
+// SFU-based variants used by the tensor-core (TF32) kernels, where the stated bound is 5e-3 on GEMM outputs
+// and 1e-5 on the log-prob sums: ex2.approx / lg2.approx carry ~1e-7 absolute error per element here.
+__device__ __forceinline__ float logp_elem_fast(const PriorDev &p, float w) {
+  const float w2 = w * w;
+  const float a = fmaf(-p.k1, w2, p.c1);
+  if (p.kind == BBB_PRIOR_GAUSSIAN) return a;
+  const float b = fmaf(-p.k2, w2, p.c2);
+  const float m = fmaxf(a, b), d = fminf(a, b) - m;   // exp(max - m) = 1
+  return m + __logf(1.0f + __expf(d));
+}
+__device__ __forceinline__ float prior_R_fast(const PriorDev &p, float w) {
+  if (p.kind == BBB_PRIOR_GAUSSIAN) return p.inv_var1;
+  const float w2 = w * w;
+  const float a = fmaf(-p.k1, w2, p.c1), b = fmaf(-p.k2, w2, p.c2);
+  const float t = __expf(-fabsf(a - b));              // smaller responsibility / larger one
+  const float inv = __fdividef(1.0f, 1.0f + t);
+  const float big = a >= b ? p.inv_var1 : p.inv_var2, small = a >= b ? p.inv_var2 : p.inv_var1;
+  return (big + t * small) * inv;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -68,15 +68,23 @@ __device__ __forceinline__ void ctl_teardown(Ctl &c, uint32_t tmem_cols) {
 
 // ---- one quad (4 consecutive k/i elements of one weight row) ------------------------------------
 struct Quad {
-  float mu[4], sg[4];
+  float mu[4], sg[4], rho[4];
 };
 __device__ __forceinline__ void load_quad(const LinArgs &a, int64_t e, bool need_sigma, Quad &q) {
   const float4 m = __ldg(reinterpret_cast<const float4 *>(a.w_mu + e));
   q.mu[0] = m.x; q.mu[1] = m.y; q.mu[2] = m.z; q.mu[3] = m.w;
   if (need_sigma) {
     const float4 r = __ldg(reinterpret_cast<const float4 *>(a.w_rho + e));
-    q.sg[0] = softplus_f(r.x); q.sg[1] = softplus_f(r.y); q.sg[2] = softplus_f(r.z); q.sg[3] = softplus_f(r.w);
+    q.rho[0] = r.x; q.rho[1] = r.y; q.rho[2] = r.z; q.rho[3] = r.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q.sg[j] = softplus_f(q.rho[j]);
   }
+}
+// sigmoid(rho) for the rho-gradient epilogue (SFU exp + fast divide)
+__device__ __forceinline__ float sigmoid_fast(float rho) {
+  const float t = __expf(-fabsf(rho));
+  const float r = __fdividef(1.0f, 1.0f + t);
+  return rho >= 0.0f ? r : t * r;
 }
 // eps and w of sample s for the quad at linear element e (e % 4 == 0)
 __device__ __forceinline__ void sample_quad(const LinArgs &a, int s, int64_t e, const Quad &q, bool sample,
@@ -142,7 +150,7 @@ __device__ __forceinline__ void issue_block(uint32_t tmem_d, uint32_t a_saddr, u
 // forward
 // ==================================================================================================
 template <int BN, int SG, bool kLogProb>
-__global__ void __launch_bounds__(NT, 1) fwd_tc_kernel(const LinArgs a_in, int k_chunk, int n_ksplit) {
+__global__ void __launch_bounds__(NT, 2) fwd_tc_kernel(const LinArgs a_in, int k_chunk, int n_ksplit) {
   using SM = Smem<BN, SG>;
   extern __shared__ uint8_t dsm[];
   __shared__ Ctl ctl;
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_tc_kernel(const LinArgs a_in, int k
         Quad q;
         load_quad(a, e, sample || lpcta, q);
         float lsg = 0.0f;
-        if (lpcta) lsg = logf(q.sg[0]) + logf(q.sg[1]) + logf(q.sg[2]) + logf(q.sg[3]);
+        if (lpcta) lsg = __logf(q.sg[0]) + __logf(q.sg[1]) + __logf(q.sg[2]) + __logf(q.sg[3]);
 #pragma unroll
         for (int s = 0; s < SG; ++s) {
           if (s < ns) {
@@ -219,8 +227,8 @@ __global__ void __launch_bounds__(NT, 1) fwd_tc_kernel(const LinArgs a_in, int k
             sample_quad(a, s0 + s, e, q, sample, ep, w);
             st_tile4(Bs + s * SM::kB, row, chunk, w[0], w[1], w[2], w[3]);
             if (lpcta) {
-              lp[s] += logp_elem(a.prior, w[0]) + logp_elem(a.prior, w[1]) + logp_elem(a.prior, w[2]) +
-                       logp_elem(a.prior, w[3]);
+              lp[s] += logp_elem_fast(a.prior, w[0]) + logp_elem_fast(a.prior, w[1]) +
+                       logp_elem_fast(a.prior, w[2]) + logp_elem_fast(a.prior, w[3]);
               lq[s] += -4.0f * kHalfLog2Pi - lsg -
                        0.5f * (ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2] + ep[3] * ep[3]);
             }
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_tc_kernel(const LinArgs a_in, int k
 // dgrad: dx_s[b][i] = sum_o dz_s[b][o] W_s[o][i];  A = dz (K = o, natural), B[i][o] = W^T (register transpose)
 // ==================================================================================================
 template <int BN, int SG>
-__global__ void __launch_bounds__(NT, 1) dgrad_tc_kernel(const LinArgs a_in, int k_chunk, int n_ksplit) {
+__global__ void __launch_bounds__(NT, 2) dgrad_tc_kernel(const LinArgs a_in, int k_chunk, int n_ksplit) {
   using SM = Smem<BN, SG>;
   extern __shared__ uint8_t dsm[];
   __shared__ Ctl ctl;
@@ -423,7 +431,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_tc_kernel(const LinArgs a_in, int
 //   t = G - gp w R(w);  grad_mu += t;  grad_rho += sigmoid(rho) (t eps - gq / sigma)      (eps regenerated)
 // ==================================================================================================
 template <int BN, int SG>
-__global__ void __launch_bounds__(NT, 1) wgrad_tc_kernel(const LinArgs a_in) {
+__global__ void __launch_bounds__(NT, 2) wgrad_tc_kernel(const LinArgs a_in) {
   using SM = Smem<BN, SG>;
   static_assert(SG * BN * BM * 4 <= SM::kTiles, "G staging must fit in the operand buffers");
   extern __shared__ uint8_t dsm[];
@@ -550,7 +558,9 @@ __global__ void __launch_bounds__(NT, 1) wgrad_tc_kernel(const LinArgs a_in) {
         const int64_t e = o * a.in + i;
         Quad q;
         load_quad(a, e, true, q);
-        float gm[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
+        float gm[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f}, sgm[4], isg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sgm[j] = sigmoid_fast(q.rho[j]); isg[j] = __fdividef(1.0f, q.sg[j]); }
 #pragma unroll
         for (int s = 0; s < SG; ++s) {
           if (s < ns) {
@@ -561,9 +571,9 @@ __global__ void __launch_bounds__(NT, 1) wgrad_tc_kernel(const LinArgs a_in) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float t = Gv[j];
-              if (gps[s] != 0.0f) t = fmaf(-gps[s] * w[j], prior_R(a.prior, w[j]), t);
+              if (gps[s] != 0.0f) t = fmaf(-gps[s] * w[j], prior_R_fast(a.prior, w[j]), t);
               gm[j] += t;
-              gr[j] += -expm1f(-q.sg[j]) * (t * ep[j] - gqs[s] / q.sg[j]);
+              gr[j] += sgm[j] * fmaf(t, ep[j], -gqs[s] * isg[j]);
             }
           }
         }
@@ -611,7 +621,7 @@ inline int cdiv_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // K split so that the grid is about one wave of the 148 SMs; chunk is a multiple of 32
 inline void pick_ksplit(int64_t K, int tiles, int *k_chunk, int *n_ksplit) {
   const int nkb = cdiv_i(K, BK);
-  int want = tiles >= kSMs ? 1 : (kSMs + tiles - 1) / tiles;
+  int want = tiles >= 2 * kSMs ? 1 : (2 * kSMs + tiles - 1) / tiles;  // two resident CTAs per SM
   if (want > nkb) want = nkb;
   if (want < 1) want = 1;
   const int per = cdiv_i(nkb, want);

@@ -158,8 +158,9 @@ __global__ void __launch_bounds__(RT) nll_gauss_kernel(const float *__restrict__
 }
 
 __global__ void elbo_finalize_kernel(const double *logp, const double *logq, const double *kl, const double *nll,
-                                     int S, float beta, float *out4) {
+                                     int S, float beta, const float *beta_dev, float *out4) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (beta_dev) beta *= *beta_dev;
   const float nll_m = (float)(nll[0] / S);
   if (kl) {
     const float k = (float)kl[0];
@@ -259,10 +260,10 @@ extern "C" int bbb_nll_gauss(const float *out, const float *target, float sigma,
 }
 
 extern "C" int bbb_elbo_finalize(const double *logp, const double *logq, const double *kl, const double *nll,
-                                 int64_t S, float beta, float *out4, void *stream) {
+                                 int64_t S, float beta, const float *beta_dev, float *out4, void *stream) {
   BBB_CHECK_ARG(nll && out4 && S > 0, "null pointer or S <= 0");
   BBB_CHECK_ARG(kl || (logp && logq), "need kl or logp+logq");
-  elbo_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(logp, logq, kl, nll, (int)S, beta, out4);
+  elbo_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(logp, logq, kl, nll, (int)S, beta, beta_dev, out4);
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }

@@ -52,6 +52,14 @@ def _alloc_grads(params):
     return out
 
 
+def _split_beta(beta):
+    """beta as a python number, or as a device tensor (read on the device: CUDA-graph replay can then follow
+    the reference's per-minibatch schedule).  Returns (host multiplier, device scalar or None)."""
+    if isinstance(beta, torch.Tensor):
+        return 1.0, beta.detach().to(torch.float32).reshape(1)
+    return float(beta), None
+
+
 class _EpsPlan:
     """eps for one call: injected tensors (reference mode) or Philox coordinates."""
 
@@ -277,11 +285,13 @@ class _FusedELBO(torch.autograd.Function):
             L.check(L.lib().bbb_nll_gauss(L.ptr(out), L.ptr(tgt), float(sigma), S, B, Cc, 1.0 / S, L.ptr(nll),
                                           L.ptr(d_out), L.stream()), 'bbb_nll_gauss')
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
-        L.check(L.lib().bbb_elbo_finalize(L.ptr(logp), L.ptr(logq), None, L.ptr(nll), S, float(beta), L.ptr(out4),
-                                          L.stream()), 'bbb_elbo_finalize')
+        beta_h, beta_d = _split_beta(beta)
+        L.check(L.lib().bbb_elbo_finalize(L.ptr(logp), L.ptr(logq), None, L.ptr(nll), S, beta_h, L.ptr(beta_d),
+                                          L.ptr(out4), L.stream()), 'bbb_elbo_finalize')
         if need_grad:
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *eps.tensors())
-        ctx.cfg = (prior, S, float(beta), tf32, eps, len(params))
+        ctx.cfg = (prior, S, beta_h, tf32, eps, len(params))
+        ctx.beta_dev = beta_d
         loss, lp, lq, nl = out4[0:1], out4[1], out4[2], out4[3:4]
         ctx.mark_non_differentiable(lp, lq, nl)
         return loss, lp, lq, nl
@@ -294,8 +304,9 @@ class _FusedELBO(torch.autograd.Function):
         params = [tuple(_f32c(t) for t in sv[2 + 4 * i:6 + 4 * i]) for i in range(nl)]
         ys = list(sv[2 + 4 * nl:2 + 4 * nl + nl - 1]) + [None]
         scale = _f32c(g_loss).reshape(1)
+        bd = ctx.beta_dev
         _, grads = _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S,
-                                    None, None, 0, scale, False)
+                                    bd, bd, 0, scale, False)
         flat = [g for lg in grads for g in lg]
         return (None,) * 8 + tuple(flat)
 
@@ -489,11 +500,13 @@ class _FusedELBOLR(torch.autograd.Function):
             L.check(L.lib().bbb_nll_gauss(L.ptr(out), L.ptr(tgt), float(sigma), S, B, Cc, 1.0 / S, L.ptr(nll),
                                           L.ptr(d_out), L.stream()), 'bbb_nll_gauss')
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
-        L.check(L.lib().bbb_elbo_finalize(None, None, L.ptr(kl), L.ptr(nll), S, float(beta), L.ptr(out4),
+        beta_h, beta_d = _split_beta(beta)
+        L.check(L.lib().bbb_elbo_finalize(None, None, L.ptr(kl), L.ptr(nll), S, beta_h, L.ptr(beta_d), L.ptr(out4),
                                           L.stream()), 'bbb_elbo_finalize')
         if need_grad:
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *deltas, *eps.tensors())
-        ctx.cfg = (sigma_p, S, float(beta), eps, len(params))
+        ctx.cfg = (sigma_p, S, beta_h, eps, len(params))
+        ctx.beta_dev = beta_d
         loss, klm, nl = out4[0:1], out4[1], out4[2:3]
         ctx.mark_non_differentiable(klm, nl)
         return loss, klm, nl
@@ -508,8 +521,8 @@ class _FusedELBOLR(torch.autograd.Function):
         ys = list(sv[o:o + nl - 1]) + [None]
         deltas = list(sv[o + nl - 1:o + 2 * nl - 1])
         scale = _f32c(g_loss).reshape(1)
-        _, grads = _net_lr_backward(x2, ys, deltas, d_out, params, sigma_p, S, eps, True, True, beta, None, scale,
-                                    False)
+        _, grads = _net_lr_backward(x2, ys, deltas, d_out, params, sigma_p, S, eps, True, True, beta, ctx.beta_dev,
+                                    scale, False)
         flat = [g for lg in grads for g in lg]
         return (None,) * 7 + tuple(flat)
 

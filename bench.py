@@ -49,6 +49,7 @@ def parse():
     ap.add_argument('--workload', default='mnist', choices=sorted(WORKLOADS))
     ap.add_argument('--samples', type=int, default=0, help='override S (MC samples per step per job)')
     ap.add_argument('--tf32', type=int, default=-1, help='1: tcgen05 kind::tf32 path, 0: exact fp32 FMA, -1: default')
+    ap.add_argument('--eager', action='store_true', help='time the eager call sequence instead of the captured graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget-s', type=float, default=25.0)
     return ap.parse_args()
@@ -301,7 +302,7 @@ def run_b200(args):
     torch.manual_seed(0)
     net = bnn_b200.BayesianNetwork(mp).to(dev)
     net.train()
-    opt = torch.optim.Adam(net.parameters(), lr=w['lr'])
+    opt = bnn_b200.FusedAdam(net.parameters(), lr=w['lr'])
     bnn_b200.manual_seed(2)
     bnn_b200.set_sample_base(rank * S)          # disjoint Philox sample indices per rank
     x_h, y_h = make_inputs(w, torch)
@@ -322,20 +323,39 @@ def run_b200(args):
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    def timed_steps(n, e2e):
+    # eager call sequence first (also the per-step launch count), then capture the same step into a CUDA graph
+    for _ in range(3):
+        step(x_d, y_d)
+    torch.cuda.synchronize()
+    l0 = L.lib().bbb_launch_count()
+    step(x_d, y_d)
+    launches_per_step = int(L.lib().bbb_launch_count() - l0)
+    graphed, graph_note = None, 'eager call sequence (--eager)'
+    if not args.eager:
+        try:
+            graphed = bnn_b200.GraphedTrainStep(net, opt, x_d, y_d, S, sigma=sigma, beta=beta, world_size=world)
+            graph_note = 'whole step captured in one CUDA graph (bnn_b200.GraphedTrainStep), one replay per step'
+        except Exception as e:          # e.g. a collective that cannot be captured: fall back to the eager sequence
+            graphed, graph_note = None, f'eager call sequence (graph capture failed: {type(e).__name__}: {e})'
+
+    def run_step(x, y):
+        if graphed is not None:
+            return graphed(x, y)[0]
+        return step(x if x.is_cuda else x.to(dev, non_blocking=True), y if y.is_cuda else y.to(dev, non_blocking=True))
+
+    def timed_steps(n, e2e, fn=None):
         """n steps; each step bracketed by CUDA events, L2 flushed between steps outside the brackets."""
+        fn = fn or run_step
         evs = []
         for _ in range(n):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if e2e:
-                xd = x_h.to(dev, non_blocking=True)
-                yd = y_h.to(dev, non_blocking=True)
-                loss = step(xd, yd)
+                loss = fn(x_h, y_h)              # pinned host -> device copies are part of the step
                 loss_h.copy_(loss.detach(), non_blocking=True)
             else:
-                step(x_d, y_d)
+                fn(x_d, y_d)
             e1.record()
             if e2e:
                 e1.synchronize()                 # the caller reads the loss every step
@@ -349,7 +369,6 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     timed_steps(max(3, args.warmup), False)
-    launches0 = L.lib().bbb_launch_count()
     barrier()
     clocks = Clocks(local) if rank == 0 else None
     t0 = time.perf_counter()
@@ -357,7 +376,13 @@ def run_b200(args):
     barrier()
     t1 = time.perf_counter()
     clk = clocks.stop(t0, t1) if clocks else None
-    launches = (L.lib().bbb_launch_count() - launches0) // max(1, args.steps)
+    launches = launches_per_step * args.steps
+    eager_ms = None
+    if graphed is not None and rank == 0 and world == 1:
+        eager = lambda x, y: step(x, y)
+        timed_steps(3, False, eager)
+        el = timed_steps(min(args.steps, 50), False, eager)
+        eager_ms = sum(el) / len(el)
     timed_steps(3, True)
     barrier()
     ms_e2e = timed_steps(args.steps, True)
@@ -442,10 +467,12 @@ def run_b200(args):
                 steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, steps_per_s=1e3 / ms,
                 higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='tf32' if tf32 else 'f32', data='synthetic',
-                config=dict(workload=workload_name(args.workload, w, S), optimizer='Adam (torch.optim, foreach)',
+                config=dict(workload=workload_name(args.workload, w, S), optimizer='Adam, one fused multi-tensor launch (bnn_b200.FusedAdam, same update rule as torch.optim.Adam)',
                             parallelism=f'MC samples sharded over {world} GPU(s), disjoint Philox sample indices'
                                         + (', NCCL all-reduce of the mu/rho gradients' if world > 1 else ''),
                             l2='flushed between timed steps (256 MiB write), flush outside the CUDA-event brackets',
+                            step=graph_note, launches_per_step=launches_per_step,
+                            eager_api_ms_per_step=eager_ms,
                             eps='Philox4x32-10 in registers, regenerated in backward',
                             gemm='tcgen05 kind::tf32' if tf32 else 'fp32 FMA (exact mode)'),
                 e2e=dict(value=e2e_v, unit='batch*MC samples/s', ms_per_step=ms2,

@@ -156,7 +156,18 @@ int bbb_nll_gauss(const float *out, const float *target, float sigma, int64_t S,
  * out4 = { beta kl + nll/S, kl, nll/S, 0 }                                              (kl != NULL)
  */
 int bbb_elbo_finalize(const double *logp, const double *logq, const double *kl, const double *nll,
-                      int64_t S, float beta, float *out4, void *stream);
+                      int64_t S, float beta, const float *beta_dev, float *out4, void *stream);
+/* beta_dev (nullable): device scalar multiplied into `beta`, so a captured CUDA graph can follow the
+ * reference's per-minibatch beta schedule (reg_task.py:63) without re-capture. */
+
+/* ---- optimiser: torch.optim.Adam.step() over all parameter tensors in ONE launch ----
+ * replaces torch.optim.Adam at reg_task.py:53,73 / class_task.py:60,79 / bandits.py:36,50 (same update rule:
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)).
+ * params/grads/exp_avg/exp_avg_sq/sizes are HOST arrays of n_tensors (<= 32) device pointers / element counts.
+ * t = step + (step_dev ? *step_dev : 0) is the 1-based Adam step; lr is multiplied by *lr_scale_dev if given. */
+int bbb_adam_step(int32_t n_tensors, float *const *params, const float *const *grads, float *const *exp_avg,
+                  float *const *exp_avg_sq, const int64_t *sizes, float lr, float beta1, float beta2, float eps,
+                  uint32_t step, const uint32_t *step_dev, const float *lr_scale_dev, void *stream);
 
 /* *counter += inc  (advances a bbb_rng.step_dev between steps; one tiny launch, graph-capturable) */
 int bbb_counter_add(uint32_t *counter, uint32_t inc, void *stream);

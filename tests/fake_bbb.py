@@ -238,8 +238,10 @@ class FakeLib:
                 G[s] = (scale * g).astype(np.float32)
         return 0
 
-    def bbb_elbo_finalize(self, logp, logq, kl, nll, S, beta, out4, st):
+    def bbb_elbo_finalize(self, logp, logq, kl, nll, S, beta, beta_dev, out4, st):
         O = _f(out4, 4)
+        if beta_dev:
+            beta = beta * float(_f(beta_dev, 1)[0])
         nm = np.float32(_d(nll, 1)[0] / S)
         if kl:
             k = np.float32(_d(kl, 1)[0])
@@ -248,6 +250,19 @@ class FakeLib:
             lp = np.float32(_d(logp, S).astype(np.float32).astype(np.float64).mean())
             lq = np.float32(_d(logq, S).astype(np.float32).astype(np.float64).mean())
             O[:] = [np.float32(beta) * lq - np.float32(beta) * lp + nm, lp, lq, nm]
+        return 0
+
+    def bbb_adam_step(self, n, params, grads, exp_avg, exp_avg_sq, sizes, lr, b1, b2, eps, step, step_dev, lr_scale_dev, st):
+        t = step + (int(_arr(step_dev, C.c_uint32, 1)[0]) if step_dev else 0)
+        if lr_scale_dev:
+            lr = lr * float(_f(lr_scale_dev, 1)[0])
+        bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+        for i in range(n):
+            k = sizes[i]
+            p, g, m, v = (_f(tab[i], k) for tab in (params, grads, exp_avg, exp_avg_sq))
+            m[...] = b1 * m + (1 - b1) * g
+            v[...] = b2 * v + (1 - b2) * g * g
+            p[...] = p - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + eps)
         return 0
 
     def bbb_counter_add(self, counter, inc, st):

@@ -1,0 +1,68 @@
+"""GPU tests of the step-level pieces: FusedAdam and the CUDA-graph train step."""
+import numpy as np
+import pytest
+import torch
+
+import bnn_b200
+from tests import parity_cases as PC
+from tests.golden_util import Case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def test_fused_adam_matches_torch_adam_on_gpu():
+    torch.manual_seed(0)
+    shapes = [(1200, 784), (1200,), (10, 1200), (10,), (3, 5), (7,)]     # includes unaligned tails
+    ps = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.Adam(ps, lr=1e-3)
+    opt = bnn_b200.FusedAdam(qs, lr=1e-3)
+    for it in range(5):
+        for p, q in zip(ps, qs):
+            g = torch.randn(p.shape, device=DEV)
+            p.grad, q.grad = g.clone(), g.clone()
+        ref.step()
+        opt.step()
+    for p, q in zip(ps, qs):
+        assert torch.allclose(p, q, rtol=2e-6, atol=1e-7), float((p - q).abs().max())
+        assert torch.allclose(ref.state[p]['exp_avg_sq'], opt.state[q]['exp_avg_sq'], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize('name,tf32', [('cfg4_bandit', False), ('small_cls_mix', False), ('cfg2_mnist_mix', True),
+                                       ('small_lr_cls', False)])
+def test_graphed_step_equals_eager_steps(name, tf32):
+    """3 replays of the captured step == 3 eager steps with the same Philox coordinates and FusedAdam;
+    capture/warm-up must leave the model untouched."""
+    c = Case(name)
+    x = c.x.to(DEV)
+    y = c.y.to(DEV) if c.mode == 'classification' else torch.randn(c.B, c.dims[-1], device=DEV)
+    seed, step0, warm = 321, 100, 2
+
+    net_g = PC.build_net(c, DEV, tf32=tf32).train()
+    opt_g = bnn_b200.FusedAdam(net_g.parameters(), lr=1e-3)
+    bnn_b200.manual_seed(seed, step0)
+    before = [p.detach().clone() for p in net_g.parameters()]
+    gs = bnn_b200.GraphedTrainStep(net_g, opt_g, x, y, c.S, sigma=c.sigma, beta=c.beta, warmup=warm)
+    for p, b in zip(net_g.parameters(), before):
+        assert torch.equal(p, b)
+    losses_g = []
+    for k in range(3):
+        info = gs(x, y, beta=c.beta)
+        losses_g.append(float(info[0]))
+
+    net_e = PC.build_net(c, DEV, tf32=tf32).train()
+    opt_e = bnn_b200.FusedAdam(net_e.parameters(), lr=1e-3)
+    bnn_b200.manual_seed(seed, step0 + warm)          # the capture consumed `warm` + 1 host steps; it baked step0 + warm
+    losses_e = []
+    elbo = net_e.sample_elbo_lr if c.lr else net_e.sample_elbo
+    for k in range(3):
+        net_e.zero_grad()
+        info = elbo(x, y, c.beta, c.S, sigma=c.sigma)
+        info[0].backward()
+        opt_e.step()
+        losses_e.append(float(info[0].detach()))
+    np.testing.assert_allclose(losses_g, losses_e, rtol=1e-5 if not tf32 else 1e-4)
+    for p, q in zip(net_g.parameters(), net_e.parameters()):
+        assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), float((p - q).abs().max())
+    assert losses_g[0] != losses_g[1]                   # fresh eps every replay

@@ -94,3 +94,34 @@ def test_product_does_not_import_oracle():
         if p.endswith('.py'):
             src = open(p).read()
             assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+def test_fused_adam_matches_torch_adam(fake):
+    """FusedAdam (host logic + ABI semantics through the double) == torch.optim.Adam over several steps."""
+    torch.manual_seed(0)
+    shapes = [(7, 5), (5,), (3, 4), (10,)]
+    ps = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.Adam(ps, lr=3e-3)
+    opt = bnn_b200.FusedAdam(qs, lr=3e-3)
+    for it in range(4):
+        for p, q in zip(ps, qs):
+            g = torch.randn(p.shape)
+            p.grad, q.grad = g.clone(), g.clone()
+        ref.step()
+        opt.step()
+    for p, q in zip(ps, qs):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+
+
+def test_beta_may_be_a_tensor(fake):
+    c = Case('small_cls_mix')
+    outs = []
+    for beta in (c.beta, torch.tensor([c.beta])):
+        net = PC.build_net(c, 'cpu').train()
+        with bnn_b200.eps_mode('reference'):
+            torch.manual_seed(5)
+            info = net.sample_elbo(c.x, c.y, beta, c.S)
+        info[0].backward()
+        outs.append((float(info[0].detach()), net.l2.weight_rho.grad.clone()))
+    assert outs[0][0] == outs[1][0] and torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-9)
