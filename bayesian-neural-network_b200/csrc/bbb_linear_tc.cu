@@ -146,6 +146,75 @@ __device__ __forceinline__ void issue_block(uint32_t tmem_d, uint32_t a_saddr, u
   for (int kk = 0; kk < 4; ++kk) mma_tf32(tmem_d, da + 2u * kk, db + 2u * kk, idesc, (first && kk == 0) ? 0u : 1u);
 }
 
+
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// Drain the SG accumulators [128][BN] of a CTA from TMEM and write them row-major to global memory with
+// coalesced 16-byte accesses.  TMEM hands every thread one ROW (lane) at a time, global memory wants a warp
+// on consecutive COLUMNS, so the tile goes through shared memory (the operand buffers, free once the MMAs
+// have completed) in a layout whose 16-byte chunk index is XORed with (row & 7): both the row-wise writes
+// and the column-wise reads are bank-conflict free.  Split-K partial sums are combined with
+// red.global.add.v4.f32 (one request per 16 bytes instead of one per float).
+template <int BN, int SG, class Bias>
+__device__ __forceinline__ void drain_tile(uint8_t *tiles, uint32_t tmem, int ns, bool have_acc, float *dst,
+                                           int64_t sample_stride, int64_t row0, int64_t rows, int64_t col0,
+                                           int64_t ld, bool vec_ok, bool atomic, float scale, Bias bias) {
+  constexpr int NCH = BN / 4, CH = ((NCH + 7) / 8) * 8, PITCH = CH * 16, HALF = BN / 2;
+  static_assert(SG * BM * PITCH <= Smem<BN, SG>::kTiles, "drain staging must fit in the operand buffers");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2, row = q4 * 32 + lane;
+#pragma unroll
+  for (int s = 0; s < SG; ++s) {
+    if (s >= ns) break;
+    uint8_t *Ys = tiles + s * BM * PITCH + row * PITCH;
+#pragma unroll
+    for (int c0 = 0; c0 < HALF; c0 += 8) {
+      const int col = half * HALF + c0;
+      float v[8];
+      if (have_acc) {
+        tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * BN + col), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(scale, v[j], bias(s, col + j));
+      const int c = col >> 2;
+      *reinterpret_cast<float4 *>(Ys + (((c) ^ (row & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4 *>(Ys + (((c + 1) ^ (row & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < SG; ++s) {
+    if (s >= ns) break;
+    float *out = dst + (int64_t)s * sample_stride;
+    for (int idx = tid; idx < BM * NCH; idx += NT) {
+      const int r = idx / NCH, c = idx % NCH;
+      const int64_t gr = row0 + r, gc = col0 + c * 4;
+      if (gr >= rows || gc >= ld) continue;
+      const float4 v = *reinterpret_cast<const float4 *>(tiles + s * BM * PITCH + r * PITCH + ((c ^ (r & 7)) << 4));
+      float *p = out + gr * ld + gc;
+      if (vec_ok && gc + 3 < ld) {
+        if (atomic) red_add_v4(p, v);
+        else *reinterpret_cast<float4 *>(p) = v;
+      } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gc + j < ld) {
+            if (atomic) atomicAdd(p + j, e[j]);
+            else p[j] = e[j];
+          }
+      }
+    }
+  }
+}
+
 // ==================================================================================================
 // forward
 // ==================================================================================================
@@ -257,36 +326,12 @@ __global__ void __launch_bounds__(NT, 2) fwd_tc_kernel(const LinArgs a_in, int k
   tc_fence_after_sync();
   __syncthreads();  // bias_s
 
-  // epilogue: warp w drains lanes 32*(w&3).., column half (w>>2)
-  const int q4 = warp & 3, half = warp >> 2;
-  const int64_t b = m0 + q4 * 32 + lane;
-  constexpr int HALF = BN / 2;
-#pragma unroll
-  for (int s = 0; s < SG; ++s) {
-    if (s >= ns) break;
-    float *ys = a.y + (int64_t)(s0 + s) * a.B * a.out;
-#pragma unroll
-    for (int c0 = 0; c0 < HALF; c0 += 8) {
-      const int col = half * HALF + c0;
-      float v[8];
-      if (nkb > 0) {
-        tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * BN + col), v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-      }
-      if (b < a.B) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int64_t o = o0 + col + j;
-          if (o < a.out) {
-            const float r = v[j] + (ksplit == 0 ? bias_s[s][col + j] : 0.0f);
-            if (n_ksplit > 1) atomicAdd(ys + b * a.out + o, r);
-            else ys[b * a.out + o] = r;
-          }
-        }
-      }
-    }
+  // epilogue: TMEM -> swizzled smem -> coalesced 16-byte stores / red.v4 (split-K)
+  {
+    const bool add_bias = ksplit == 0;
+    drain_tile<BN, SG>(tiles, tmem, ns, nkb > 0, a.y + (int64_t)s0 * a.B * a.out, a.B * a.out, m0, a.B, o0, a.out,
+                       a.vec_out, n_ksplit > 1, 1.0f,
+                       [&](int s, int c) { return add_bias ? bias_s[s][c] : 0.0f; });
   }
   if (lpcta) {
 #pragma unroll
@@ -393,36 +438,9 @@ __global__ void __launch_bounds__(NT, 2) dgrad_tc_kernel(const LinArgs a_in, int
   mbar_wait(smem_u32(&ctl.bar[2]), 0);
   tc_fence_after_sync();
 
-  const int q4 = warp & 3, half = warp >> 2;
-  const int64_t b = m0 + q4 * 32 + lane;
-  constexpr int HALF = BN / 2;
   const float osc = ((a.flags & BBB_F_SCALE_DX) && a.out_scale_dev) ? __ldg(a.out_scale_dev) : 1.0f;
-#pragma unroll
-  for (int s = 0; s < SG; ++s) {
-    if (s >= ns) break;
-    float *dxs = a.dx + (int64_t)(s0 + s) * a.B * a.in;
-#pragma unroll
-    for (int c0 = 0; c0 < HALF; c0 += 8) {
-      const int col = half * HALF + c0;
-      float v[8];
-      if (nkb > 0) {
-        tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * BN + col), v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-      }
-      if (b < a.B) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int64_t i = i0 + col + j;
-          if (i < a.in) {
-            if (n_ksplit > 1) atomicAdd(dxs + b * a.in + i, osc * v[j]);
-            else dxs[b * a.in + i] = osc * v[j];
-          }
-        }
-      }
-    }
-  }
+  drain_tile<BN, SG>(tiles, tmem, ns, nkb > 0, a.dx + (int64_t)s0 * a.B * a.in, a.B * a.in, m0, a.B, i0, a.in, a.vec_in,
+                     n_ksplit > 1, osc, [](int, int) { return 0.0f; });
   ctl_teardown(ctl, SM::kTmemCols);
 }
 
@@ -451,11 +469,19 @@ __global__ void __launch_bounds__(NT, 2) wgrad_tc_kernel(const LinArgs a_in) {
   ctl_setup(ctl, SM::kTmemCols);
   const uint32_t tmem = ctl.tmem_base;
   float *Gs = reinterpret_cast<float *>(tiles);  // [SG][BN][128] after the MMAs of a group have completed
+  __shared__ float colsum_s[SG][BN];             // sum_b dz[b][o] (bias gradients), first i tile only
 
   int it_global = 0;  // pipeline iteration counter across sample groups (mbarrier phases keep running)
   const int ngroups = (a.S + SG - 1) / SG;
   for (int g = 0; g < ngroups; ++g) {
     const int s0 = g * SG, ns = min(SG, a.S - s0);
+    float bsum[SG][4];
+#pragma unroll
+    for (int s = 0; s < SG; ++s) bsum[s][0] = bsum[s][1] = bsum[s][2] = bsum[s][3] = 0.0f;
+    if (bias_cta && tid < BN) {
+#pragma unroll
+      for (int s = 0; s < SG; ++s) colsum_s[s][tid] = 0.0f;
+    }
     for (int it = 0; it < nkb; ++it, ++it_global) {
       const int stage = it_global & 1;
       if (it >= 2) mbar_wait(smem_u32(&ctl.bar[stage]), (uint32_t)(((it_global >> 1) - 1) & 1));
@@ -493,6 +519,12 @@ __global__ void __launch_bounds__(NT, 2) wgrad_tc_kernel(const LinArgs a_in) {
               v[r] = ld_row4(a.dy + base, b0 + bq * 4 + r, o0 + oq * 4, a.B, a.out, a.vec_out);
               if (a.mask) v[r] = mask4(v[r], ld_row4(a.mask + base, b0 + bq * 4 + r, o0 + oq * 4, a.B, a.out, a.vec_out));
             }
+            if (bias_cta) {  // each thread owns at most one (oq, bq) block: keep its column sums in registers
+              bsum[s][0] += v[0].x + v[1].x + v[2].x + v[3].x;
+              bsum[s][1] += v[0].y + v[1].y + v[2].y + v[3].y;
+              bsum[s][2] += v[0].z + v[1].z + v[2].z + v[3].z;
+              bsum[s][3] += v[0].w + v[1].w + v[2].w + v[3].w;
+            }
             uint8_t *T = Bs + s * SM::kB;
             st_tile4(T, oq * 4 + 0, bq, v[0].x, v[1].x, v[2].x, v[3].x);
             st_tile4(T, oq * 4 + 1, bq, v[0].y, v[1].y, v[2].y, v[3].y);
@@ -512,6 +544,13 @@ __global__ void __launch_bounds__(NT, 2) wgrad_tc_kernel(const LinArgs a_in) {
                         idesc, it == 0);
         mma_commit(smem_u32(&ctl.bar[stage]));
       }
+    }
+    if (bias_cta && tid < 8 * (BN / 4)) {
+      const int oq = tid % (BN / 4);
+#pragma unroll
+      for (int s = 0; s < SG; ++s)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(&colsum_s[s][oq * 4 + c], bsum[s][c]);
     }
     // all MMAs of this group done -> operand buffers are free, accumulators are final
     if (tid == 0) mma_commit(smem_u32(&ctl.bar[2]));
@@ -590,13 +629,7 @@ __global__ void __launch_bounds__(NT, 2) wgrad_tc_kernel(const LinArgs a_in) {
       if (o < a.out) {
         float gbm = 0.0f, gbr = 0.0f;
         for (int s = 0; s < ns; ++s) {
-          const int64_t base = (int64_t)(s0 + s) * a.B * a.out;
-          float colsum = 0.0f;
-          for (int64_t b = 0; b < a.B; ++b) {
-            float v = __ldg(a.dy + base + b * a.out + o);
-            if (a.mask && !(__ldg(a.mask + base + b * a.out + o) > 0.0f)) v = 0.0f;
-            colsum += v;
-          }
+          const float colsum = colsum_s[s][tid];
           float bv, sg, ep;
           bias_elem(a, s0 + s, o, sample, true, bv, sg, ep);
           float t = colsum;
@@ -621,7 +654,7 @@ inline int cdiv_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // K split so that the grid is about one wave of the 148 SMs; chunk is a multiple of 32
 inline void pick_ksplit(int64_t K, int tiles, int *k_chunk, int *n_ksplit) {
   const int nkb = cdiv_i(K, BK);
-  int want = tiles >= 2 * kSMs ? 1 : (2 * kSMs + tiles - 1) / tiles;  // two resident CTAs per SM
+  int want = tiles >= kSMs ? 1 : (kSMs + tiles / 2) / tiles;  // about one CTA per SM: every split costs a red pass
   if (want > nkb) want = nkb;
   if (want < 1) want = 1;
   const int per = cdiv_i(nkb, want);
