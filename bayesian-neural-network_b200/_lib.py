@@ -22,7 +22,7 @@ class Prior(C.Structure):
     _fields_ = [('kind', C.c_int32), ('pi', C.c_float), ('sigma1', C.c_float), ('sigma2', C.c_float)]
 
 
-P, I64, I32, F32, U32, U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint32, C.c_uint64
+P, I64, I32, F32, F64, U32, U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_double, C.c_uint32, C.c_uint64
 _SIGS = {
     'bbb_version': ([], C.c_int),
     'bbb_last_error_string': ([], C.c_char_p),
@@ -39,7 +39,7 @@ _SIGS = {
     'bbb_nll_ce': ([P, P, I64, I64, I64, F32, P, P, P], C.c_int),
     'bbb_nll_gauss': ([P, P, F32, I64, I64, I64, F32, P, P, P], C.c_int),
     'bbb_elbo_finalize': ([P, P, P, P, I64, F32, P, P, P], C.c_int),
-    'bbb_adam_step': ([I32, P, P, P, P, P, F32, F32, F32, F32, U32, P, P, P], C.c_int),
+    'bbb_adam_step': ([I32, P, P, P, P, P, F64, F64, F64, F64, U32, P, P, P], C.c_int),
     'bbb_counter_add': ([P, U32, P], C.c_int),
 }
 EXPORTS = tuple(_SIGS)

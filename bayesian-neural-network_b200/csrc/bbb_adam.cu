@@ -19,25 +19,36 @@ struct AdamArgs {
   int64_t qend[kMaxTensors];  // cumulative quads (ceil(size/4)) up to and including this tensor
   bool vec[kMaxTensors];      // all four pointers 16-byte aligned
   int n;
-  float lr, b1, b2, eps;
+  double lr, b1, b2;  // torch forms 1-b, the bias corrections and the step size in double: so does the kernel
+  float eps;
   uint32_t step;
   const uint32_t *step_dev;
   const float *lr_scale_dev;
 };
 
-__device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, float b1, float b2, float step_size,
-                                      float inv_sqrt_bc2, float eps) {
-  m = fmaf(b1, m, (1.0f - b1) * g);
-  v = fmaf(b2, v, (1.0f - b2) * g * g);
-  const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
-  p -= step_size * (m / denom);
+struct AdamConst {
+  float b1, b2, omb1, omb2, step_size, bc2_sqrt, eps;
+};
+// lerp_(g, 1-b1);  mul_(b2).addcmul_(g, g, 1-b2);  denom = sqrt(v)/sqrt(bc2) + eps;  addcdiv_(m, denom, -step_size)
+__device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, const AdamConst &c) {
+  m = fmaf(c.omb1, g - m, m);
+  v = fmaf(c.omb2 * g, g, c.b2 * v);
+  const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
+  p = fmaf(-c.step_size, m / denom, p);
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
-  const uint32_t t = a.step + (a.step_dev ? *a.step_dev : 0u);
-  const float bc1 = 1.0f - powf(a.b1, (float)t), bc2 = 1.0f - powf(a.b2, (float)t);
-  const float lr = a.lr * (a.lr_scale_dev ? *a.lr_scale_dev : 1.0f);
-  const float step_size = lr / bc1, inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+  __shared__ AdamConst cs;
+  if (threadIdx.x == 0) {  // one double-precision evaluation per block, as torch does on the host
+    const uint32_t t = a.step + (a.step_dev ? *a.step_dev : 0u);
+    const double bc1 = 1.0 - pow(a.b1, (double)t), bc2 = 1.0 - pow(a.b2, (double)t);
+    const double lr = a.lr * (a.lr_scale_dev ? (double)*a.lr_scale_dev : 1.0);
+    cs.b1 = (float)a.b1; cs.b2 = (float)a.b2;
+    cs.omb1 = (float)(1.0 - a.b1); cs.omb2 = (float)(1.0 - a.b2);
+    cs.step_size = (float)(lr / bc1); cs.bc2_sqrt = (float)sqrt(bc2); cs.eps = a.eps;
+  }
+  __syncthreads();
+  const AdamConst c = cs;
   const int64_t total = a.qend[a.n - 1], stride = (int64_t)gridDim.x * blockDim.x;
   int ti = 0;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
@@ -49,17 +60,17 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     if (valid == 4 && a.vec[ti]) {
       float4 P = *reinterpret_cast<float4 *>(pp), M = *reinterpret_cast<float4 *>(pm), V = *reinterpret_cast<float4 *>(pv);
       const float4 G = *reinterpret_cast<const float4 *>(pg);
-      adam1(P.x, G.x, M.x, V.x, a.b1, a.b2, step_size, inv_sqrt_bc2, a.eps);
-      adam1(P.y, G.y, M.y, V.y, a.b1, a.b2, step_size, inv_sqrt_bc2, a.eps);
-      adam1(P.z, G.z, M.z, V.z, a.b1, a.b2, step_size, inv_sqrt_bc2, a.eps);
-      adam1(P.w, G.w, M.w, V.w, a.b1, a.b2, step_size, inv_sqrt_bc2, a.eps);
+      adam1(P.x, G.x, M.x, V.x, c);
+      adam1(P.y, G.y, M.y, V.y, c);
+      adam1(P.z, G.z, M.z, V.z, c);
+      adam1(P.w, G.w, M.w, V.w, c);
       *reinterpret_cast<float4 *>(pp) = P;
       *reinterpret_cast<float4 *>(pm) = M;
       *reinterpret_cast<float4 *>(pv) = V;
     } else {
       for (int j = 0; j < valid; ++j) {
         float P = pp[j], M = pm[j], V = pv[j];
-        adam1(P, pg[j], M, V, a.b1, a.b2, step_size, inv_sqrt_bc2, a.eps);
+        adam1(P, pg[j], M, V, c);
         pp[j] = P; pm[j] = M; pv[j] = V;
       }
     }
@@ -72,8 +83,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
 using namespace bbb;
 
 extern "C" int bbb_adam_step(int32_t n_tensors, float *const *params, const float *const *grads, float *const *exp_avg,
-                             float *const *exp_avg_sq, const int64_t *sizes, float lr, float beta1, float beta2,
-                             float eps, uint32_t step, const uint32_t *step_dev, const float *lr_scale_dev,
+                             float *const *exp_avg_sq, const int64_t *sizes, double lr, double beta1, double beta2,
+                             double eps, uint32_t step, const uint32_t *step_dev, const float *lr_scale_dev,
                              void *stream) {
   BBB_CHECK_ARG(n_tensors >= 0 && n_tensors <= kMaxTensors, "0 <= n_tensors <= 32");
   BBB_CHECK_ARG(n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && sizes), "null table");
@@ -94,7 +105,7 @@ extern "C" int bbb_adam_step(int32_t n_tensors, float *const *params, const floa
     ++n;
   }
   if (n == 0) return BBB_OK;
-  a.n = n; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.step = step; a.step_dev = step_dev;
+  a.n = n; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = (float)eps; a.step = step; a.step_dev = step_dev;
   a.lr_scale_dev = lr_scale_dev;
   int64_t blocks = (q + 255) / 256;
   const int64_t cap = (int64_t)kSMs * 8;

@@ -164,9 +164,10 @@ int bbb_elbo_finalize(const double *logp, const double *logq, const double *kl, 
  * replaces torch.optim.Adam at reg_task.py:53,73 / class_task.py:60,79 / bandits.py:36,50 (same update rule:
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)).
  * params/grads/exp_avg/exp_avg_sq/sizes are HOST arrays of n_tensors (<= 32) device pointers / element counts.
- * t = step + (step_dev ? *step_dev : 0) is the 1-based Adam step; lr is multiplied by *lr_scale_dev if given. */
+ * t = step + (step_dev ? *step_dev : 0) is the 1-based Adam step; lr is multiplied by *lr_scale_dev if given.
+ * The hyper-parameters are doubles because torch forms 1-beta, the bias corrections and the step size in double. */
 int bbb_adam_step(int32_t n_tensors, float *const *params, const float *const *grads, float *const *exp_avg,
-                  float *const *exp_avg_sq, const int64_t *sizes, float lr, float beta1, float beta2, float eps,
+                  float *const *exp_avg_sq, const int64_t *sizes, double lr, double beta1, double beta2, double eps,
                   uint32_t step, const uint32_t *step_dev, const float *lr_scale_dev, void *stream);
 
 /* *counter += inc  (advances a bbb_rng.step_dev between steps; one tiny launch, graph-capturable) */
