@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, 'libbbb.so')
 
 # flags (include/bbb.h)
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
+F_OUT_ZEROED, F_DX_PREACT = 256, 512
 PRIOR_GAUSSIAN, PRIOR_MIXTURE = 0, 1
 
 

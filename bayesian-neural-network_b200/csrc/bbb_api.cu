@@ -19,8 +19,8 @@ extern "C" int bbb_linear_fwd(const float *x, int64_t x_sample_stride, const flo
                               const float *b_mu, const float *b_rho, const float *eps_w, const float *eps_b,
                               const bbb_rng *rng, const bbb_prior *prior, int64_t S, int64_t B, int64_t in,
                               int64_t out, int32_t flags, float *y, double *logp, double *logq, void *stream) {
-  BBB_CHECK_ARG(x && w_mu && b_mu && y, "null pointer");
   BBB_CHECK_ARG(S >= 0 && B >= 0 && in >= 0 && out >= 0 && S <= 65535, "bad shape");
+  BBB_CHECK_ARG(w_mu && b_mu && ((x && y) || S * B == 0), "null pointer");  // empty batches carry null activations
   BBB_CHECK_ARG(x_sample_stride == 0 || x_sample_stride == B * in, "x_sample_stride must be 0 or B*in");
   const bool sample = flags & BBB_F_SAMPLE, lpq = flags & BBB_F_LOGPROB;
   BBB_CHECK_ARG(!(sample || lpq) || (w_rho && b_rho), "rho pointers required");
@@ -38,6 +38,7 @@ extern "C" int bbb_linear_fwd(const float *x, int64_t x_sample_stride, const flo
   a.vec_in = (in % 4 == 0) && all16({x, w_mu, w_rho, eps_w});
   a.vec_out = (out % 4 == 0) && all16({y});
   cudaStream_t st = (cudaStream_t)stream;
+  if ((flags & BBB_F_TF32) && linear_sk_supported(a)) return launch_linear_fwd_sk(a, st);
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_fwd_tc(a, st);
   return launch_linear_fwd_fma(a, st);
 }
@@ -49,10 +50,11 @@ extern "C" int bbb_linear_bwd(const float *dy, const float *dy_mask_src, const f
                               const float *gp_dev, const float *gq_dev, int64_t g_dev_stride,
                               const float *out_scale_dev, float *dx, float *grad_w_mu, float *grad_w_rho,
                               float *grad_b_mu, float *grad_b_rho, void *stream) {
-  BBB_CHECK_ARG(dy && x && w_mu && w_rho && b_mu && b_rho, "null pointer");
+  BBB_CHECK_ARG(w_mu && w_rho && b_mu && b_rho && ((dy && x) || S * B == 0), "null pointer");
   BBB_CHECK_ARG((flags & BBB_F_NO_WGRAD) || (grad_w_mu && grad_w_rho && grad_b_mu && grad_b_rho),
                 "null gradient pointer");
-  BBB_CHECK_ARG((flags & BBB_F_NO_DX) || dx, "dx required unless BBB_F_NO_DX");
+  BBB_CHECK_ARG((flags & BBB_F_NO_DX) || dx || S * B == 0, "dx required unless BBB_F_NO_DX");
+  BBB_CHECK_ARG(!(flags & BBB_F_DX_PREACT) || (flags & BBB_F_RELU_IN), "BBB_F_DX_PREACT needs BBB_F_RELU_IN");
   BBB_CHECK_ARG(S >= 0 && B >= 0 && in >= 0 && out >= 0 && S <= 65535, "bad shape");
   BBB_CHECK_ARG(x_sample_stride == 0 || x_sample_stride == B * in, "x_sample_stride must be 0 or B*in");
   const bool sample = flags & BBB_F_SAMPLE;
@@ -74,6 +76,8 @@ extern "C" int bbb_linear_bwd(const float *dy, const float *dy_mask_src, const f
   a.vec_out = (out % 4 == 0) && all16({dy, dy_mask_src});
   if (S == 0 || B == 0) a.S = (B == 0) ? a.S : 0;  // degenerate: gradients reduce to the prior/posterior terms
   cudaStream_t st = (cudaStream_t)stream;
+  if ((flags & BBB_F_TF32) && a.S > 0 && linear_bwd_fused_supported(a)) return launch_linear_bwd_fused(a, st);
+  if ((flags & BBB_F_TF32) && a.S > 0 && linear_sk_supported(a)) return launch_linear_bwd_sk(a, st);
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_bwd_tc(a, st);
   return launch_linear_bwd_fma(a, st);
 }

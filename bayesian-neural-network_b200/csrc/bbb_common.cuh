@@ -42,6 +42,7 @@ struct PriorDev {
   int kind;
   float c1, k1, inv_var1;  // component 1: log(pi) - log(s1) - .5log2pi ; 1/(2 s1^2) ; 1/s1^2
   float c2, k2, inv_var2;  // component 2 (mixture only)
+  float c1l, k1l, c2l, k2l;  // c and k times log2(e): the density terms in the base the SFU works in
 };
 
 inline PriorDev make_prior_dev(const bbb_prior *p) {
@@ -61,6 +62,9 @@ inline PriorDev make_prior_dev(const bbb_prior *p) {
     d.k1 = (float)(1.0 / (2.0 * s1 * s1));
     d.inv_var1 = (float)(1.0 / (s1 * s1));
   }
+  const double l2e = 1.4426950408889634074;
+  d.c1l = (float)(d.c1 * l2e); d.k1l = (float)(d.k1 * l2e);
+  d.c2l = (float)(d.c2 * l2e); d.k2l = (float)(d.k2 * l2e);
   return d;
 }
 
@@ -201,6 +205,61 @@ __device__ __forceinline__ float prior_R_fast(const PriorDev &p, float w) {
   const float inv = __fdividef(1.0f, 1.0f + t);
   const float big = a >= b ? p.inv_var1 : p.inv_var2, small = a >= b ? p.inv_var2 : p.inv_var1;
   return (big + t * small) * inv;
+}
+
+// ---------------------------------------------------------------------------------------
+// SFU math for the tensor-core (TF32) kernels.  Stated bounds for that mode: 5e-3 on anything downstream of a
+// contraction, 1e-5 on the log-prob sums; every function below is accurate to ~1e-6 relative or better.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigma = log1p(t), t = e^rho, plus sigmoid(rho) = t / (1 + t) from the same exponential.
+// t < 1/8: alternating series to t^6 (truncation 5e-7 relative); else log(1 + t) on the SFU; rho > 15: sigma = rho.
+__device__ __forceinline__ void softplus_sigmoid_fast(float rho, float &sigma, float &sigmoid) {
+  const float t = ex2_approx(rho * 1.4426950408889634f);
+  const float u = 1.0f + t;
+  float ser = fmaf(t, -0.16666667f, 0.2f);
+  ser = fmaf(t, ser, -0.25f);
+  ser = fmaf(t, ser, 0.33333334f);
+  ser = fmaf(t, ser, -0.5f);
+  ser = fmaf(t, ser, 1.0f);
+  ser *= t;
+  const float lg = 0.6931471805599453f * lg2_approx(u);
+  sigma = rho > 15.0f ? rho : (t < 0.125f ? ser : lg);
+  sigmoid = rho > 15.0f ? 1.0f : __fdividef(t, u);
+}
+__device__ __forceinline__ float softplus_fast(float rho) {
+  float sg, sm;
+  softplus_sigmoid_fast(rho, sg, sm);
+  return sg;
+}
+// sum of log p(w_j) over the 4 weights of a quad.  Mixture: p = 2^a + 2^b in the base-2 domain, one lg2 per PAIR of
+// weights (the product of two densities cannot underflow for |w| < 9 sigma1); same exp -> mix -> log order as
+// networks.py:24-27.
+__device__ __forceinline__ float logp_quad_fast(const PriorDev &p, const float w[4]) {
+  if (p.kind == BBB_PRIOR_GAUSSIAN) {
+    const float s2 = fmaf(w[0], w[0], fmaf(w[1], w[1], fmaf(w[2], w[2], w[3] * w[3])));
+    return fmaf(-p.k1, s2, 4.0f * p.c1);
+  }
+  float d[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float w2 = w[j] * w[j];
+    d[j] = ex2_approx(fmaf(-p.k1l, w2, p.c1l)) + ex2_approx(fmaf(-p.k2l, w2, p.c2l));
+  }
+  return 0.6931471805599453f * (lg2_approx(d[0] * d[1]) + lg2_approx(d[2] * d[3]));
+}
+// sum of log sigma_j over a quad: one lg2 per pair (sigma > 1e-19 keeps the product normal)
+__device__ __forceinline__ float logsigma_quad_fast(const float sg[4]) {
+  return 0.6931471805599453f * (lg2_approx(sg[0] * sg[1]) + lg2_approx(sg[2] * sg[3]));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -40,6 +40,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// same, for waits that are expected to be long (a warp whose only job is to wait for producers): the suspend-time
+// hint lets the hardware park the thread instead of re-issuing the poll, which would steal issue slots
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+  }
+}
 
 // ---- fences -----------------------------------------------------------------------------
 // generic-proxy smem writes (st.shared by the staging threads) -> visible to the async proxy (tcgen05.mma)
@@ -84,6 +98,29 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 }
 __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// same with operand major-ness: bit 15 = A is MN-major, bit 16 = B is MN-major (0 = K-major)
+__host__ __device__ constexpr uint32_t idesc_tf32_major(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+  return idesc_tf32(M, N) | (a_mn << 15) | (b_mn << 16);
+}
+// MN-major kind::tf32 operands exist in ONE shared-memory format, SWIZZLE_128B_BASE32B (layout type 1; probed on
+// B200 with tools/mma_probe.cu, and what CUTLASS' builder states: "for mn-major tf32 operands, SW128_32B is the only
+// available smem layout").  The matrix is stored as stacked regions of [K rows][128 bytes = 32 MN elements]; inside
+// a row the 32-BYTE chunk index is XORed with (row & 3); swizzle atoms are 4 K rows tall.
+//   LBO = byte distance between consecutive 32-element MN groups (regions), SBO = 512 = distance between consecutive
+//   4-row K atoms.  Advancing K by 8 (one MMA) = +1024 bytes on the start address.
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)1u << 61;
+  return d;
+}
+// byte offset of the 16-byte chunk `c16` (0..7) of row `row` inside one such region
+__device__ __forceinline__ uint32_t mn32_off(int row, int c16) {
+  return (uint32_t)((row << 7) + ((((c16 >> 1) ^ row) & 3) << 5) + ((c16 & 1) << 4));
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, one K = 8 slice; issued by ONE thread

@@ -28,9 +28,8 @@ def make_prior(prior_init, mixture_prior):
     return L.Prior(L.PRIOR_GAUSSIAN, 0.0, float(prior_init[0]), 0.0)
 
 
-def _rng(layer, seed, step):
-    dev = R.device_step()
-    return L.Rng(seed, step, R.get_sample_base(), layer, L.ptr(dev))
+def _rng(layer, seed, step, sample_base, step_dev):
+    return L.Rng(seed, step, sample_base, layer, L.ptr(step_dev))
 
 
 def _f32c(t):
@@ -65,6 +64,9 @@ class _EpsPlan:
 
     def __init__(self, injected=None, seed=0, step=0):
         self.injected, self.seed, self.step = injected, seed, step
+        # every RNG coordinate is pinned when the forward runs: the backward executes on autograd's own thread,
+        # where the thread-local settings of rng.py (sample base, device step counter) are not the caller's
+        self.sample_base, self.step_dev = R.get_sample_base(), R.device_step()
 
     def ptrs(self, l):
         if self.injected is None:
@@ -72,7 +74,7 @@ class _EpsPlan:
         return L.ptr(self.injected[l][0]), L.ptr(self.injected[l][1])
 
     def rng(self, l):
-        return _rng(l, self.seed, self.step)
+        return _rng(l, self.seed, self.step, self.sample_base, self.step_dev)
 
     def tensors(self):
         return [] if self.injected is None else [t for pair in self.injected.values() for t in pair]
@@ -122,42 +124,56 @@ def _ws_bwd(dy, mask, x, x_stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev
                                    L.stream()), 'bbb_linear_bwd')
 
 
+def _zeroed_views(shapes, device):
+    """One zero-filled buffer carved into tensors of the given shapes (a single memset for all of them): the
+    split-K tensor-core kernels add partial tiles into their output with red.add (BBB_F_OUT_ZEROED)."""
+    sizes = [int(torch.Size(sh).numel()) for sh in shapes]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+    out, off = [], 0
+    for sh, n in zip(shapes, sizes):
+        out.append(flat[off:off + n].view(sh))
+        off += n
+    return out
+
+
 def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq):
     """All layers, all S samples.  Returns the list of pre-activation outputs ys[l] = [S,B,out_l]."""
     B = x2.shape[0]
-    ys = []
-    base = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if logprob else 0) | (L.F_TF32 if tf32 else 0)
+    base = ((L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if logprob else 0) | (L.F_TF32 if tf32 else 0) |
+            L.F_OUT_ZEROED)
+    ys = _zeroed_views([(S, B, p[0].shape[0]) for p in params], x2.device)
     inp, stride = x2, 0
     for l, p in enumerate(params):
         out, inn = p[0].shape
-        y = torch.empty((S, B, out), dtype=torch.float32, device=x2.device)
-        _ws_fwd(inp, stride, p, eps, l, prior, S, B, base | (L.F_RELU_IN if l > 0 else 0), y, logp, logq)
-        ys.append(y)
-        inp, stride = y, B * out
+        _ws_fwd(inp, stride, p, eps, l, prior, S, B, base | (L.F_RELU_IN if l > 0 else 0), ys[l], logp, logq)
+        inp, stride = ys[l], B * out
     return ys
 
 
 def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq, gp_dev, gq_dev, g_stride,
                      out_scale, need_dx0):
-    """Backward of _net_ws_forward.  Returns (dx0 or None, [grads per layer])."""
+    """Backward of _net_ws_forward.  Returns (dx0 or None, [grads per layer]).  Every layer above the first
+    hands down the gradient w.r.t. the PRE-activation output of the layer below (BBB_F_DX_PREACT: the ReLU mask
+    is applied where dx is produced), so no layer needs a separate mask pass over dy."""
     B = x2.shape[0]
-    base = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0)
+    base = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0) | L.F_OUT_ZEROED
     grads = _alloc_grads(params)
     dy, dx0 = d_out, None
+    first = 0 if need_dx0 else 1
+    dxs = [None] * first + _zeroed_views([(S, B, p[0].shape[1]) for p in params[first:]], x2.device)
     for l in reversed(range(len(params))):
         p = params[l]
         out, inn = p[0].shape
         g = grads[l]
-        flags = base | (L.F_RELU_IN if l > 0 else 0)
+        flags = base | ((L.F_RELU_IN | L.F_DX_PREACT) if l > 0 else 0)
         want_dx = l > 0 or need_dx0
-        dx = torch.empty((S, B, inn), dtype=torch.float32, device=x2.device) if want_dx else None
+        dx = dxs[l] if want_dx else None
         if not want_dx:
             flags |= L.F_NO_DX
         if l == 0 and need_dx0:
             flags |= L.F_SCALE_DX
-        mask = ys[l] if l + 1 < len(params) else None
         x_in, stride = (x2, 0) if l == 0 else (ys[l - 1], B * inn)
-        _ws_bwd(dy, mask, x_in, stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev, gq_dev, g_stride, out_scale,
+        _ws_bwd(dy, None, x_in, stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev, gq_dev, g_stride, out_scale,
                 dx, g)
         dy = dx
         if l == 0:

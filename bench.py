@@ -249,8 +249,8 @@ class CallTimer:
             return r
 
         def call(*a):
-            if name in ('bbb_linear_bwd', 'bbb_lr_linear_bwd'):
-                fi = 16 if name == 'bbb_linear_bwd' else 17
+            if name == 'bbb_lr_linear_bwd':          # the LR backward is two kernels: time them one by one
+                fi = 17
                 flags = a[fi]
                 r = 0
                 if not flags & L.F_NO_DX:
@@ -259,7 +259,7 @@ class CallTimer:
                 b = list(a); b[fi] = flags | L.F_NO_DX
                 r |= timed(name + ':wgrad', *b)
                 return r
-            return timed(name, *a)
+            return timed(name, *a)                   # bbb_linear_bwd is ONE fused kernel (dgrad + wgrad)
         return call
 
 
@@ -276,7 +276,8 @@ def kernel_bytes(tag, a, L):
         act = 4 * S * B * out + mask + 4 * B * inn * (1 if x_shared else S)
         if tag.endswith(':dgrad'):
             return S * 8 * inn * out + 4 * S * B * out + mask + 4 * S * B * inn
-        return S * 8 * inn * out + 8 * inn * out + act
+        dx = 0 if (a[16 if tag.startswith('bbb_linear_bwd') else 17] & L.F_NO_DX) else 4 * S * B * inn
+        return S * 8 * inn * out + 8 * inn * out + act + (dx if not tag.endswith(':wgrad') else 0)
     return None
 
 
@@ -296,7 +297,8 @@ def run_b200(args):
 
     w = dict(WORKLOADS[args.workload])
     S = args.samples or w['S']                 # per-GPU MC samples (weak scaling over the sample axis)
-    tf32 = (args.tf32 == 1)
+    # default: the tcgen05 kind::tf32 path where the layers are wide enough to be dense contractions
+    tf32 = (args.tf32 == 1) or (args.tf32 < 0 and args.workload in ('mnist', 'wide'))
     mp = model_params(w)
     mp['tf32'] = tf32
     torch.manual_seed(0)

@@ -51,6 +51,10 @@ extern "C" {
 #define BBB_F_NO_DX 32     /* backward: do not compute dx                                      */
 #define BBB_F_SCALE_DX 64  /* backward: out_scale_dev also multiplies dx                       */
 #define BBB_F_NO_WGRAD 128 /* backward: do not compute parameter gradients (dx only)           */
+#define BBB_F_DX_PREACT 512 /* backward, with BBB_F_RELU_IN: dx is multiplied by (x > 0), i.e. it is the gradient
+                              w.r.t. the PRE-activation input; the layer below then needs no dy_mask_src      */
+#define BBB_F_OUT_ZEROED 256 /* y (forward) / dx (backward) is already zero-filled by the caller: kernels that
+                               combine split-K partial sums with red.add skip their own memset              */
 
 /* Philox tensor ids: weight tensor of layer l -> 2l, bias -> 2l+1, LR activation noise -> 2l */
 typedef struct bbb_rng {

@@ -14,6 +14,7 @@ import numpy as np
 from oracle import closed_form as CF
 
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
+F_OUT_ZEROED, F_DX_PREACT = 256, 512
 
 
 def _arr(ptr, ctype, *shape):
@@ -98,6 +99,7 @@ class FakeLib:
             gps = gp * (float(GPD[s * gstride]) if gp_dev else 1.0)
             gqs = gq * (float(GQD[s * gstride]) if gq_dev else 1.0)
             xs_ = X[s if xs else 0]
+            x_pre = xs_
             if relu:
                 xs_ = np.maximum(xs_, 0)
             dz = DY[s] * (MK[s] > 0) if mask else DY[s]
@@ -113,7 +115,11 @@ class FakeLib:
             a_bm += tb
             a_br += CF.sigmoid(BR) * (tb * e_b - gqs / sb)
             if DX is not None:
-                DX[s] = ((dz @ w) * (osc if flags & F_SCALE_DX else 1.0)).astype(np.float32)
+                d = (dz @ w) * (osc if flags & F_SCALE_DX else 1.0)
+                if flags & F_DX_PREACT:
+                    assert relu
+                    d = d * (x_pre > 0)
+                DX[s] = d.astype(np.float32)
         for ptr, shape, val in ((gwm, (out, inn), a_wm), (gwr, (out, inn), a_wr), (gbm, (out,), a_bm),
                                 (gbr, (out,), a_br)):
             G = _f(ptr, *shape)
@@ -166,6 +172,7 @@ class FakeLib:
         DX = _f(dx, S, B, inn) if not (flags & F_NO_DX) else None
         for s in range(S):
             xs_ = X[s if xs else 0]
+            x_pre = xs_
             if relu:
                 xs_ = np.maximum(xs_, 0)
             dz = DY[s] * (MK[s] > 0) if mask else DY[s]

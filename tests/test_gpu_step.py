@@ -64,5 +64,13 @@ def test_graphed_step_equals_eager_steps(name, tf32):
         losses_e.append(float(info[0].detach()))
     np.testing.assert_allclose(losses_g, losses_e, rtol=1e-5 if not tf32 else 1e-4)
     for p, q in zip(net_g.parameters(), net_e.parameters()):
-        assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), float((p - q).abs().max())
+        if not tf32:
+            assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), float((p - q).abs().max())
+        else:
+            # the tensor-core kernels combine split-K partial tiles with fp32 red.add, whose order varies from run to
+            # run; Adam's first steps move every weight by +-lr whatever the gradient's size, so a weight whose
+            # gradient is pure round-off can step the other way.  Allow a vanishing fraction of such sign flips.
+            bad = ~torch.isclose(p, q, rtol=1e-4, atol=2e-6)
+            assert bad.float().mean() <= 1e-4, float(bad.float().mean())
+            assert float((p - q).abs().max()) <= 3 * 2 * 1e-3 * 1.01
     assert losses_g[0] != losses_g[1]                   # fresh eps every replay
