@@ -133,6 +133,17 @@ __global__ void __launch_bounds__(NT2, kCtaPerSm) fwd_sk_kernel(const LinArgs a_
   float lp[SG], lq[SG];
 #pragma unroll
   for (int s = 0; s < SG; ++s) lp[s] = lq[s] = 0.0f;
+  // thread t owns row t/8, 16-byte chunk t%8 of the weight tile and rows t/8 + 32 j of the activation tile; in the
+  // SWIZZLE_128B layout row r and row r + 32 share (r & 7), so one offset (+ 4096 j) serves all of them
+  const int wrow = tid >> 3, chunk = tid & 7;
+  const uint32_t w_off = sw128_off(wrow, chunk);
+  int xrow_off[4];
+  bool xrow_ok[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    xrow_ok[j] = wrow + 32 * j < a.B;
+    xrow_off[j] = (wrow + 32 * j) * (int)a.in;
+  }
 
   if (warp == NPW) {
     mma_warp<BN, SG>(ctl, tiles, tmem, u0, u1, nkb, o_tiles, a.S, x_shared);
@@ -157,32 +168,54 @@ __global__ void __launch_bounds__(NT2, kCtaPerSm) fwd_sk_kernel(const LinArgs a_
           bias_s[s][tid] = bv;
         }
       }
+      // Per-thread constants of the segment.  Thread t samples the weight quad (row t/8, chunk t%8) of every unit and
+      // stages the activation chunks (rows t/8 + 32 j, chunk t%8): the shared-memory slots are the same in every
+      // stage and the global addresses advance by 32 floats per unit, so the unit loop carries no index arithmetic.
+      const int64_t o = o0 + wrow;
+      const bool o_ok = tid < BN * 8 && o < a.out;
+      const int64_t e_row = o * a.in + chunk * 4;
+      float4 nmu = make_float4(0.f, 0.f, 0.f, 0.f), nrho = nmu;
+      if (o_ok && kb0 * BK + chunk * 4 < a.in) {
+        nmu = __ldg(reinterpret_cast<const float4 *>(a.w_mu + e_row + (int64_t)kb0 * BK));
+        if (sample || kLogProb) nrho = __ldg(reinterpret_cast<const float4 *>(a.w_rho + e_row + (int64_t)kb0 * BK));
+      }
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int stage = it % NS;
         if (it >= NS) mbar_wait(smem_u32(&ctl.empty[stage]), (uint32_t)(((it / NS) - 1) & 1));
         uint8_t *As = tiles + stage * R::kStage, *Bs = As + SG * A_TILE;
-        const int64_t kbase = (int64_t)kb * BK;
+        const int kc = kb * BK + chunk * 4;
+        const bool col_ok = kc < a.in;
         // activation loads are issued first and consumed after the sampling below has covered their latency
         float4 xv[SG][4];
 #pragma unroll
         for (int s = 0; s < SG; ++s) {
           if (s < ns && (s == 0 || !x_shared)) {
-            const float *xs = a.x + (int64_t)(s0 + s) * a.x_sstride;
+            const float *xs = a.x + (int64_t)(s0 + s) * a.x_sstride + kc;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int idx = tid + NTP * j;
-              xv[s][j] = ld_row4(xs, idx >> 3, kbase + (idx & 7) * 4, a.B, a.in, true);
+              const bool ok = col_ok && xrow_ok[j];
+              const float4 v = __ldg(reinterpret_cast<const float4 *>(ok ? xs + xrow_off[j] : a.x));
+              xv[s][j] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
         }
+        // this unit's mu/rho arrived during the previous unit; the next unit's are requested now
+        const float4 cmu = nmu, crho = nrho;
+        if (o_ok && kb + 1 < kb1 && kc + BK < a.in) {
+          nmu = __ldg(reinterpret_cast<const float4 *>(a.w_mu + e_row + (int64_t)(kb + 1) * BK));
+          if (sample || kLogProb) nrho = __ldg(reinterpret_cast<const float4 *>(a.w_rho + e_row + (int64_t)(kb + 1) * BK));
+        }
         // weights: [BN out rows][32 k] per sample, formed in registers
-        for (int idx = tid; idx < BN * 8; idx += NTP) {
-          const int row = idx >> 3, chunk = idx & 7;
-          const int64_t o = o0 + row, k = kbase + chunk * 4;
-          if (o < a.out && k < a.in) {
-            const int64_t e = o * a.in + k;
+        if (tid < BN * 8) {
+          if (o_ok && col_ok) {
+            const int64_t e = e_row + (int64_t)kb * BK;
             Quad q;
-            load_quad(a, e, sample || kLogProb, q);
+            q.mu[0] = cmu.x; q.mu[1] = cmu.y; q.mu[2] = cmu.z; q.mu[3] = cmu.w;
+            q.rho[0] = crho.x; q.rho[1] = crho.y; q.rho[2] = crho.z; q.rho[3] = crho.w;
+            if (sample || kLogProb) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) q.sg[c] = softplus_fast(q.rho[c]);
+            }
             float lsg = 0.0f;
             if (kLogProb) lsg = logsigma_quad_fast(q.sg);
 #pragma unroll
@@ -190,7 +223,8 @@ __global__ void __launch_bounds__(NT2, kCtaPerSm) fwd_sk_kernel(const LinArgs a_
               if (s < ns) {
                 float ep[4], w[4];
                 sample_quad(a, s0 + s, e, q, sample, ep, w);
-                st_tile4(Bs + s * R::kB, row, chunk, w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<float4 *>(Bs + s * R::kB + w_off) =
+                    make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
                 if (kLogProb) {
                   lp[s] += logp_quad_fast(a.prior, w);
                   lq[s] += -4.0f * kHalfLog2Pi - lsg -
@@ -201,19 +235,16 @@ __global__ void __launch_bounds__(NT2, kCtaPerSm) fwd_sk_kernel(const LinArgs a_
           } else {
 #pragma unroll
             for (int s = 0; s < SG; ++s)
-              if (s < ns) st_tile4(Bs + s * R::kB, row, chunk, 0.f, 0.f, 0.f, 0.f);
+              if (s < ns) *reinterpret_cast<float4 *>(Bs + s * R::kB + w_off) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        // activations go in as they are: the tensor core reads the upper 19 bits of each fp32 (TF32 by truncation)
 #pragma unroll
         for (int s = 0; s < SG; ++s) {
           if (s < ns && (s == 0 || !x_shared)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int idx = tid + NTP * j;
-              float4 v = xv[s][j];
-              if (relu) v = relu4(v);
-              st_tile4(As + s * A_TILE, idx >> 3, idx & 7, v.x, v.y, v.z, v.w);
-            }
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4 *>(As + s * A_TILE + w_off + 4096 * j) = relu ? relu4(xv[s][j]) : xv[s][j];
           }
         }
         fence_proxy_async_smem();
