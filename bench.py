@@ -281,6 +281,16 @@ def kernel_bytes(tag, a, L):
     return None
 
 
+def finish(dist, torch):
+    """Leave together.  The captured step graph holds NCCL work; the graphs and the communicator are torn down by
+    process exit rather than by destroy_process_group(), which was seen to block behind them."""
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -314,11 +324,11 @@ def run_b200(args):
     loss_h = torch.empty(1, pin_memory=True)
     elbo = net.sample_elbo_lr if w['lrp'] else net.sample_elbo
 
-    def step(x, y):
+    def step(x, y, collective=True):
         net.zero_grad()
         loss = elbo(x, y, beta, S, sigma=sigma)[0]
         loss.backward()
-        if world > 1:
+        if world > 1 and collective:
             parallel.allreduce_gradients(net, world)
         opt.step()
         return loss
@@ -408,12 +418,12 @@ def run_b200(args):
         L._lib = prox
         try:
             for _ in range(3):
-                step(x_d, y_d)
+                step(x_d, y_d, collective=False)       # rank 0 alone: no collective in this diagnostic pass
             prox.records.clear()
             reps = 20
             for _ in range(reps):
                 flush.zero_()
-                step(x_d, y_d)
+                step(x_d, y_d, collective=False)
             torch.cuda.synchronize()
         finally:
             L._lib = real
@@ -445,7 +455,7 @@ def run_b200(args):
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            finish(dist, torch)
         return
 
     alg = algorithmic(w, S)
@@ -484,7 +494,7 @@ def run_b200(args):
                 kernels=kern_table, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        finish(dist, torch)
 
 
 def main():
