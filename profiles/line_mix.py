@@ -13,7 +13,7 @@ for r in rows:
         continue
     if len(r) > 8 and r[0].isdigit() and r[7].isdigit():      # a source line row: Line No, Source, ..., # Samples, Instr Exec
         n = int(r[7]); tot += n
-        out.append((n, int(r[6] or 0), cur, int(r[0]), r[1].strip()[:110]))
+        out.append((n, int(r[6]) if r[6].isdigit() else 0, cur, int(r[0]), r[1].strip()[:110]))
 out.sort(reverse=True)
 print('total executed warp instructions', tot)
 for n, samp, f, ln, src in out[:top]:
