@@ -38,6 +38,8 @@ __device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, con
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ AdamConst cs;
   if (threadIdx.x == 0) {  // one double-precision evaluation per block, as torch does on the host
     const uint32_t t = a.step + (a.step_dev ? *a.step_dev : 0u);
@@ -110,7 +112,7 @@ extern "C" int bbb_adam_step(int32_t n_tensors, float *const *params, const floa
   int64_t blocks = (q + 255) / 256;
   const int64_t cap = (int64_t)kSMs * 8;
   if (blocks > cap) blocks = cap;
-  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  BBB_CHECK_CUDA(launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a));
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }

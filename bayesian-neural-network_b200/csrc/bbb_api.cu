@@ -77,7 +77,6 @@ extern "C" int bbb_linear_bwd(const float *dy, const float *dy_mask_src, const f
   if (S == 0 || B == 0) a.S = (B == 0) ? a.S : 0;  // degenerate: gradients reduce to the prior/posterior terms
   cudaStream_t st = (cudaStream_t)stream;
   if ((flags & BBB_F_TF32) && a.S > 0 && linear_bwd_fused_supported(a)) return launch_linear_bwd_fused(a, st);
-  if ((flags & BBB_F_TF32) && a.S > 0 && linear_sk_supported(a)) return launch_linear_bwd_sk(a, st);
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_bwd_tc(a, st);
   return launch_linear_bwd_fma(a, st);
 }

@@ -32,6 +32,33 @@ void note_launch(int n = 1);  // diagnostic launch counter (bbb_launch_count)
   } while (0)
 
 // ---------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The kernels of a train step form one dependent chain; launched with the
+// programmatic-serialisation attribute, kernel N+1 becomes resident while kernel N drains and runs its prologue
+// (shared-memory carve-up, TMEM allocation, barrier init) until pdl_wait(), which returns when every prerequisite
+// grid has completed and its memory is visible.  Every kernel launched through launch_pdl() calls pdl_wait() before
+// it touches global memory, and pdl_launch_dependents() first thing (all grids here fit in one wave, so letting
+// the successor in early cannot starve the running grid).  Without the attribute both are no-ops.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------
 // constants
 // ---------------------------------------------------------------------------------------
 constexpr float kHalfLog2Pi = 0.918938533204672741780329736406f;

@@ -58,11 +58,9 @@ bool linear_tc_supported(const LinArgs &a);
 int launch_linear_fwd_tc(const LinArgs &a, cudaStream_t st);
 int launch_linear_bwd_tc(const LinArgs &a, cudaStream_t st);
 
-// tcgen05 kind::tf32 path for batches of at most 128 rows (bbb_linear_sk.cu): stream-K forward / dgrad,
-// balanced-slab wgrad, two co-resident CTAs per SM.
+// tcgen05 kind::tf32 forward for batches of at most 128 rows (bbb_linear_sk.cu): stream-K, two co-resident CTAs per SM.
 bool linear_sk_supported(const LinArgs &a);
 int launch_linear_fwd_sk(const LinArgs &a, cudaStream_t st);
-int launch_linear_bwd_sk(const LinArgs &a, cudaStream_t st);
 
 // fused backward (wgrad + analytic epilogue + dgrad, one eps regeneration) for batches of at most 128 rows
 // (bbb_linear_bwd_fused.cu)

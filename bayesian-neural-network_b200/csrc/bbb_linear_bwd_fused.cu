@@ -31,14 +31,15 @@ using namespace tcx;
 
 constexpr int FT = 512;              // threads per CTA (16 warps, one CTA per SM)
 constexpr int REG = 128 * 128;       // bytes of one [128 rows][128 B] swizzled region
-constexpr int DZ_REGS = 4;           // dz tile: 128 o columns
-constexpr int XW_REGS = 3;           // x tile / Wt tile: 96 i columns
-constexpr int NWIN = XW_REGS * 32;   // MMA N
-constexpr int WMAX = 88;             // widest column range a CTA may own
+constexpr int DZ_REGS = 4;           // dz tile: up to 128 o columns (only the regions the row tile needs are staged)
+constexpr int XW_MAX = 3;            // x tile / Wt tile: XWR regions of 32 i columns, XWR = 1, 2 or 3 (template)
 constexpr int QMAX = 6;              // weight quads per thread: 512 * 6 * 4 >= 128 * 88
-constexpr int kFusedDyn = (2 * DZ_REGS + 2 * XW_REGS) * REG + 1024;  // dz (MN) | dz (K) | x | Wt
-constexpr uint32_t kFusedTmemCols = 256;  // G: columns [0, 96), dX: columns [128, 224)
-static_assert(FT * QMAX * 4 >= 128 * WMAX, "every own weight needs a thread slot");
+constexpr uint32_t kFusedTmemCols = 256;  // G: columns [0, 32 XWR), dX: columns [128, 128 + 32 XWR)
+// widest column range a CTA may own with XWR regions: the window is 32 XWR wide and starts at the range's first
+// column, so the whole window could be owned; 8 columns are kept free so that ranges stay comfortably inside
+constexpr int wmax_of(int xwr) { return 32 * xwr - 8; }
+constexpr int fused_dyn(int xwr) { return (2 * DZ_REGS + 2 * xwr) * REG + 1024; }  // dz (MN) | dz (K) | x | Wt
+static_assert(FT * QMAX * 4 >= 128 * wmax_of(XW_MAX), "every own weight needs a thread slot");
 
 struct FCtl {
   uint64_t bar;
@@ -53,14 +54,14 @@ __device__ __forceinline__ uint8_t *k_ptr(uint8_t *tile, int row, int col4) {
   return tile + (col4 >> 3) * REG + sw128_off(row, col4 & 7);
 }
 
-template <bool kDx>
+template <bool kDx, int XWR>
 __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, int T_o) {
+  constexpr int NWIN = 32 * XWR;  // MMA N
   extern __shared__ uint8_t dsm[];
   __shared__ FCtl ctl;
   __shared__ float csum_part[2][128];   // (the dynamic tiles leave 2 KB of the 227 KB)
   LinArgs a = a_in;
-  rng_resolve(a.rng);
-  uint8_t *dz_t = align1024(dsm), *dzk_t = dz_t + DZ_REGS * REG, *x_t = dzk_t + DZ_REGS * REG, *w_t = x_t + XW_REGS * REG;
+  uint8_t *dz_t = align1024(dsm), *dzk_t = dz_t + DZ_REGS * REG, *x_t = dzk_t + DZ_REGS * REG, *w_t = x_t + XWR * REG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN, wgrad = !(a.flags & BBB_F_NO_WGRAD);
   const bool dx_preact = a.flags & BBB_F_DX_PREACT, accum = a.flags & BBB_F_ACCUM;
@@ -75,6 +76,9 @@ __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, in
   const int64_t i_lo = (int64_t)q_lo * 4;
   const int nquad = rows * tq;
   const bool bias_cta = blockIdx.x == 0;
+  const int nzr = (rows + 31) >> 5;                // dz regions (32 o columns each) this row tile needs
+  const int st_row = tid >> 3, st_chunk = tid & 7; // staging: rows st_row + 64 h, chunk st_chunk of every region
+  const uint32_t st_mn = mn32_off(st_row, st_chunk), st_k = sw128_off(st_row, st_chunk);
 
   if (warp == 0) tmem_alloc(smem_u32(&ctl.tmem_base), kFusedTmemCols);
   if (tid == 32) {
@@ -84,6 +88,8 @@ __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, in
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  pdl_wait();              // everything above is local; from here on global memory of earlier kernels is read
+  rng_resolve(a.rng);
   const uint32_t tmem = ctl.tmem_base, tmem_g = tmem, tmem_dx = tmem + 128;
   constexpr uint32_t idesc1 = idesc_tf32_major(128, NWIN, 1, 1);  // MMA1: A = dz (MN-major), B = x (MN-major)
   constexpr uint32_t idesc2 = idesc_tf32_major(128, NWIN, 0, 1);  // MMA2: A = dz (K-major),  B = Wt (MN-major)
@@ -99,46 +105,65 @@ __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, in
   uint32_t phase = 0;
 
   for (int s = 0; s < a.S; ++s) {
-    // ---- 1. stage dz_s [128 b][128 o] and x_s [128 b][96 i] (loads first, then the swizzled stores) ----------
+    // ---- 1. stage dz_s [128 b][32 nzr o] and x_s [128 b][32 XWR i]: all loads first, then the swizzled stores.
+    // Thread t handles rows t/8 + 64 h, 16-byte chunk t%8 of every region; rows r and r + 64 share (r & 7), so the
+    // two shared-memory offsets (one per swizzle) are per-thread constants and the loops carry no index arithmetic.
     {
-      const int64_t zbase = (int64_t)s * a.B * a.out;
-      const int ncol4 = (rows + 3) >> 2;             // dz columns beyond the tile's rows are never used
-      float4 zv[8];
+      const float *dys = a.dy + (int64_t)s * a.B * a.out + o_t0 + st_chunk * 4;
+      const float *mks = a.mask ? a.mask + (int64_t)s * a.B * a.out + o_t0 + st_chunk * 4 : nullptr;
+      float4 zv[2 * DZ_REGS];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int idx = tid + FT * r, b = idx >> 5, c4 = idx & 31;
-        const int64_t o = o_t0 + c4 * 4;
-        zv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.vec_out) {
-          zv[r] = ld_row4_al(a.dy + zbase, c4 < ncol4 ? b : a.B, o, a.B, a.out);
-          if (a.mask) zv[r] = mask4(zv[r], ld_row4_al(a.mask + zbase, c4 < ncol4 ? b : a.B, o, a.B, a.out));
-        } else if (c4 < ncol4) {
-          zv[r] = ld_row4(a.dy + zbase, b, o, a.B, a.out, false);
-          if (a.mask) zv[r] = mask4(zv[r], ld_row4(a.mask + zbase, b, o, a.B, a.out, false));
+      for (int g = 0; g < DZ_REGS; ++g) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g < nzr) {
+            const int b = st_row + 64 * h;
+            const int64_t o = o_t0 + g * 32 + st_chunk * 4;
+            if (a.vec_out) {
+              const bool ok = b < B && o < a.out;
+              const float4 t = __ldg(reinterpret_cast<const float4 *>(ok ? dys + (int64_t)b * a.out + g * 32 : a.dy));
+              v = ok ? t : v;
+              if (mks) v = mask4(v, ok ? __ldg(reinterpret_cast<const float4 *>(mks + (int64_t)b * a.out + g * 32)) : v);
+            } else {
+              v = ld_row4(a.dy + (int64_t)s * a.B * a.out, b, o, a.B, a.out, false);
+              if (mks) v = mask4(v, ld_row4(a.mask + (int64_t)s * a.B * a.out, b, o, a.B, a.out, false));
+            }
+          }
+          zv[2 * g + h] = v;
         }
       }
       const bool load_x = s == 0 || a.x_sstride != 0;
-      float4 xv[6];
+      float4 xv[2 * XWR];
       if (load_x) {
-        const float *xs = a.x + (int64_t)s * a.x_sstride;
+        const float *xs = a.x + (int64_t)s * a.x_sstride + i_lo + st_chunk * 4;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const int idx = tid + FT * r, b = idx / 24, c4 = idx - b * 24;
-          xv[r] = ld_row4_al(xs, c4 < tq ? b : a.B, i_lo + c4 * 4, a.B, a.in);   // columns beyond the own range: zero
+        for (int g = 0; g < XWR; ++g) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int b = st_row + 64 * h, c4 = g * 8 + st_chunk;
+            const bool ok = b < B && c4 < tq;          // columns beyond the own range: zero
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(ok ? xs + (int64_t)b * a.in + g * 32 : a.x));
+            xv[2 * g + h] = ok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int idx = tid + FT * r;
-        const float4 v = zv[r];
-        *reinterpret_cast<float4 *>(mn_ptr(dz_t, idx >> 5, idx & 31)) = v;
-        if (kDx) *reinterpret_cast<float4 *>(k_ptr(dzk_t, idx >> 5, idx & 31)) = v;
+      for (int g = 0; g < DZ_REGS; ++g) {
+        if (g < nzr) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            *reinterpret_cast<float4 *>(dz_t + g * REG + st_mn + h * 8192) = zv[2 * g + h];
+            if (kDx) *reinterpret_cast<float4 *>(dzk_t + g * REG + st_k + h * 8192) = zv[2 * g + h];
+          }
+        }
       }
       if (load_x) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const int idx = tid + FT * r, b = idx / 24;
-          *reinterpret_cast<float4 *>(mn_ptr(x_t, b, idx - b * 24)) = relu ? relu4(xv[r]) : xv[r];
+        for (int g = 0; g < XWR; ++g) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            *reinterpret_cast<float4 *>(x_t + g * REG + st_mn + h * 8192) = relu ? relu4(xv[2 * g + h]) : xv[2 * g + h];
         }
       }
     }
@@ -162,16 +187,16 @@ __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, in
       nmu = __ldg(reinterpret_cast<const float4 *>(a.w_mu + e));
       nrho = __ldg(reinterpret_cast<const float4 *>(a.w_rho + e));
     }
-    mbar_wait(smem_u32(&ctl.bar), phase);
+    mbar_wait_parked(smem_u32(&ctl.bar), phase);
     phase ^= 1u;
     tc_fence_after_sync();
 
     // ---- 3. G: TMEM [lane = o][column = i] -> Wt layout in shared memory ------------------------------------------
     {
-      const int o_r = (warp & 3) * 32 + lane, cg = warp >> 2;   // 4 column groups of 24
+      const int o_r = (warp & 3) * 32 + lane, cg = warp >> 2;   // 4 column groups of NWIN / 4
 #pragma unroll
-      for (int c0 = 0; c0 < 24; c0 += 8) {
-        const int col = cg * 24 + c0;
+      for (int c0 = 0; c0 < NWIN / 4; c0 += 8) {
+        const int col = cg * (NWIN / 4) + c0;
         float v[8];
         tmem_ld8(tmem_g + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, v);
         *reinterpret_cast<float4 *>(mn_ptr(w_t, o_r, col >> 2)) = make_float4(v[0], v[1], v[2], v[3]);
@@ -221,7 +246,8 @@ __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, in
       }
     }
     if (kDx) {  // everything in the 128 x 96 window that is not an own weight must not contribute to dX
-      for (int idx = tid; idx < 128 * (NWIN / 4); idx += FT) {
+      const int r_up = (rows + 7) & ~7;   // MMA2 reads Wt rows in steps of 8
+      for (int idx = tid; idx < r_up * (NWIN / 4); idx += FT) {
         const int r = idx / (NWIN / 4), c4 = idx - r * (NWIN / 4);
         if (r >= rows || c4 >= tq) *reinterpret_cast<float4 *>(mn_ptr(w_t, r, c4)) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -263,7 +289,7 @@ __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, in
         mma_commit(smem_u32(&ctl.bar));
       }
       bias_finish();
-      mbar_wait(smem_u32(&ctl.bar), phase);
+      mbar_wait_parked(smem_u32(&ctl.bar), phase);
       phase ^= 1u;
       tc_fence_after_sync();
       // ---- 6. dX: TMEM [lane = b][column = i] -> (x > 0) mask -> red.add into dx --------------------------------
@@ -271,8 +297,8 @@ __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, in
         const int b = (warp & 3) * 32 + lane, cg = warp >> 2;
         float *drow = a.dx + ((int64_t)s * a.B + b) * a.in + i_lo;
 #pragma unroll
-        for (int c0 = 0; c0 < 24; c0 += 8) {
-          const int col = cg * 24 + c0;
+        for (int c0 = 0; c0 < NWIN / 4; c0 += 8) {
+          const int col = cg * (NWIN / 4) + c0;
           float v[8];
           tmem_ld8(tmem_dx + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, v);
 #pragma unroll
@@ -294,6 +320,7 @@ __global__ void __launch_bounds__(FT, 1) bwd_fused_kernel(const LinArgs a_in, in
     __syncthreads();  // the tiles and the accumulators are reused by the next sample
   }
 
+  pdl_launch_dependents();   // the sample loop is done: let the next kernel of the chain become resident
   // ---- parameter gradients ------------------------------------------------------------------------------------
   if (wgrad) {
 #pragma unroll
@@ -328,29 +355,35 @@ bool linear_bwd_fused_supported(const LinArgs &a) {
   return a.vec_in && a.in >= 4 && a.out >= 1 && a.B >= 1 && a.B <= 128 && a.S >= 1;
 }
 
+namespace {
+template <bool kDx, int XWR>
+int launch_one(const LinArgs &a, dim3 grid, int T_o, cudaStream_t st) {
+  BBB_CHECK_CUDA(cudaFuncSetAttribute(bwd_fused_kernel<kDx, XWR>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_dyn(XWR)));
+  BBB_CHECK_CUDA(launch_pdl(bwd_fused_kernel<kDx, XWR>, grid, dim3(FT), fused_dyn(XWR), st, a, T_o));
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+}  // namespace
+
 int launch_linear_bwd_fused(const LinArgs &a, cudaStream_t st) {
   const bool want_dx = !(a.flags & BBB_F_NO_DX);
   const int n_ot = cdiv_i(a.out, 128);
   const int T_o = ((cdiv_i(a.out, n_ot) + 3) / 4) * 4;         // equal row tiles; a multiple of 4 keeps dz loads vectorised
+  const int nq_i = (int)(a.in / 4);
   int n_c = kSMs / n_ot;                                       // about one CTA per SM
-  const int need = cdiv_i(a.in / 4, WMAX / 4);                 // every column range must fit the 88-column limit
+  const int need = cdiv_i(nq_i, wmax_of(XW_MAX) / 4);          // every column range must fit the widest window
   if (n_c < need) n_c = need;
-  if (n_c > a.in / 4) n_c = (int)(a.in / 4);
+  if (n_c > nq_i) n_c = nq_i;
   if (n_c < 1) n_c = 1;
+  const int width = cdiv_i(nq_i, n_c) * 4;                     // widest own column range
   dim3 grid(n_c, cdiv_i(a.out, T_o));
   if (want_dx && !(a.flags & BBB_F_OUT_ZEROED)) {
     BBB_CHECK_CUDA(cudaMemsetAsync(a.dx, 0, sizeof(float) * (size_t)a.S * a.B * a.in, st));
     note_launch();
   }
-  if (want_dx) {
-    BBB_CHECK_CUDA(cudaFuncSetAttribute(bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedDyn));
-    bwd_fused_kernel<true><<<grid, FT, kFusedDyn, st>>>(a, T_o);
-  } else {
-    BBB_CHECK_CUDA(cudaFuncSetAttribute(bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedDyn));
-    bwd_fused_kernel<false><<<grid, FT, kFusedDyn, st>>>(a, T_o);
-  }
-  BBB_CHECK_LAUNCH();
-  return BBB_OK;
+  if (width <= wmax_of(1)) return want_dx ? launch_one<true, 1>(a, grid, T_o, st) : launch_one<false, 1>(a, grid, T_o, st);
+  if (width <= wmax_of(2)) return want_dx ? launch_one<true, 2>(a, grid, T_o, st) : launch_one<false, 2>(a, grid, T_o, st);
+  return want_dx ? launch_one<true, 3>(a, grid, T_o, st) : launch_one<false, 3>(a, grid, T_o, st);
 }
 
 }  // namespace bbb

@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(128) nll_ce_kernel(const float *__restrict__ l
                                                      const int64_t *__restrict__ target, int64_t rows, int64_t B,
                                                      int64_t C, float grad_scale, double *nll,
                                                      float *__restrict__ dlogits) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float local = 0.0f;
@@ -147,6 +149,8 @@ __global__ void __launch_bounds__(RT) nll_gauss_kernel(const float *__restrict__
                                                        float inv_2var, float inv_var, float cst, int64_t n,
                                                        int64_t per_sample, float grad_scale, double *nll,
                                                        float *__restrict__ dout) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[64];
   float acc = 0.0f;
   for (int64_t i = (int64_t)blockIdx.x * RT + threadIdx.x; i < n; i += (int64_t)gridDim.x * RT) {
@@ -159,6 +163,8 @@ __global__ void __launch_bounds__(RT) nll_gauss_kernel(const float *__restrict__
 
 __global__ void elbo_finalize_kernel(const double *logp, const double *logq, const double *kl, const double *nll,
                                      int S, float beta, const float *beta_dev, float *out4) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (beta_dev) beta *= *beta_dev;
   const float nll_m = (float)(nll[0] / S);
@@ -239,8 +245,8 @@ extern "C" int bbb_nll_ce(const float *logits, const int64_t *target, int64_t S,
   BBB_CHECK_ARG(S >= 0 && B >= 0 && C > 0, "bad shape");
   const int64_t rows = S * B;
   if (rows == 0) return BBB_OK;
-  nll_ce_kernel<<<grid_for(rows, 4), 128, 0, (cudaStream_t)stream>>>(logits, target, rows, B, C, grad_scale, nll,
-                                                                     dlogits);
+  BBB_CHECK_CUDA(launch_pdl(nll_ce_kernel, dim3(grid_for(rows, 4)), dim3(128), 0, (cudaStream_t)stream, logits, target, rows, B,
+                            C, grad_scale, nll, dlogits));
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }
@@ -252,9 +258,9 @@ extern "C" int bbb_nll_gauss(const float *out, const float *target, float sigma,
   const int64_t n = S * B * D;
   if (n == 0) return BBB_OK;
   const double var = (double)sigma * sigma;
-  nll_gauss_kernel<<<grid_for(n, RT), RT, 0, (cudaStream_t)stream>>>(
-      out, target, (float)(0.5 / var), (float)(1.0 / var), (float)(log((double)sigma) + 0.918938533204672741780329736406),
-      n, B * D, grad_scale, nll, dout);
+  BBB_CHECK_CUDA(launch_pdl(nll_gauss_kernel, dim3(grid_for(n, RT)), dim3(RT), 0, (cudaStream_t)stream, out, target,
+                            (float)(0.5 / var), (float)(1.0 / var),
+                            (float)(log((double)sigma) + 0.918938533204672741780329736406), n, B * D, grad_scale, nll, dout));
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }
@@ -263,17 +269,22 @@ extern "C" int bbb_elbo_finalize(const double *logp, const double *logq, const d
                                  int64_t S, float beta, const float *beta_dev, float *out4, void *stream) {
   BBB_CHECK_ARG(nll && out4 && S > 0, "null pointer or S <= 0");
   BBB_CHECK_ARG(kl || (logp && logq), "need kl or logp+logq");
-  elbo_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(logp, logq, kl, nll, (int)S, beta, beta_dev, out4);
+  BBB_CHECK_CUDA(launch_pdl(elbo_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, logp, logq, kl, nll, (int)S, beta,
+                            beta_dev, out4));
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }
 
 namespace bbb { namespace {
-__global__ void counter_add_kernel(uint32_t *c, uint32_t inc) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += inc; }
+__global__ void counter_add_kernel(uint32_t *c, uint32_t inc) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *c += inc;
+}
 } }
 extern "C" int bbb_counter_add(uint32_t *counter, uint32_t inc, void *stream) {
   BBB_CHECK_ARG(counter, "null pointer");
-  counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, inc);
+  BBB_CHECK_CUDA(launch_pdl(counter_add_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, counter, inc));
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }
