@@ -23,6 +23,13 @@ class Prior(C.Structure):
     _fields_ = [('kind', C.c_int32), ('pi', C.c_float), ('sigma1', C.c_float), ('sigma2', C.c_float)]
 
 
+class AdamFuse(C.Structure):
+    """struct bbb_adam_fuse: optimiser state of (w_mu, w_rho, b_mu, b_rho) + hyper-parameters"""
+    _fields_ = [('exp_avg', C.c_void_p * 4), ('exp_avg_sq', C.c_void_p * 4), ('lr', C.c_double),
+                ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double), ('step', C.c_uint32),
+                ('step_dev', C.c_void_p), ('lr_scale_dev', C.c_void_p)]
+
+
 P, I64, I32, F32, F64, U32, U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_double, C.c_uint32, C.c_uint64
 _SIGS = {
     'bbb_version': ([], C.c_int),
@@ -31,6 +38,8 @@ _SIGS = {
     'bbb_linear_fwd': ([P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, P, P, P, P], C.c_int),
     'bbb_linear_bwd': ([P, P, P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, F32, F32, P, P, I64, P,
                         P, P, P, P, P, P], C.c_int),
+    'bbb_linear_bwd_adam': ([P, P, P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, F32, F32, P, P, I64, P,
+                             P, P, P], C.c_int),
     'bbb_lr_linear_fwd': ([P, I64, P, P, P, P, P, P, P, F32, I64, I64, I64, I64, I32, P, P, P, P], C.c_int),
     'bbb_lr_linear_bwd': ([P, P, P, I64, P, P, P, P, P, P, P, P, F32, I64, I64, I64, I64, I32, F32, P, P,
                            P, P, P, P, P, P], C.c_int),

@@ -26,29 +26,11 @@ struct AdamArgs {
   const float *lr_scale_dev;
 };
 
-struct AdamConst {
-  float b1, b2, omb1, omb2, step_size, bc2_sqrt, eps;
-};
-// lerp_(g, 1-b1);  mul_(b2).addcmul_(g, g, 1-b2);  denom = sqrt(v)/sqrt(bc2) + eps;  addcdiv_(m, denom, -step_size)
-__device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, const AdamConst &c) {
-  m = fmaf(c.omb1, g - m, m);
-  v = fmaf(c.omb2 * g, g, c.b2 * v);
-  const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
-  p = fmaf(-c.step_size, m / denom, p);
-}
-
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ AdamConst cs;
-  if (threadIdx.x == 0) {  // one double-precision evaluation per block, as torch does on the host
-    const uint32_t t = a.step + (a.step_dev ? *a.step_dev : 0u);
-    const double bc1 = 1.0 - pow(a.b1, (double)t), bc2 = 1.0 - pow(a.b2, (double)t);
-    const double lr = a.lr * (a.lr_scale_dev ? (double)*a.lr_scale_dev : 1.0);
-    cs.b1 = (float)a.b1; cs.b2 = (float)a.b2;
-    cs.omb1 = (float)(1.0 - a.b1); cs.omb2 = (float)(1.0 - a.b2);
-    cs.step_size = (float)(lr / bc1); cs.bc2_sqrt = (float)sqrt(bc2); cs.eps = a.eps;
-  }
+  if (threadIdx.x == 0) cs = adam_consts(a.lr, a.b1, a.b2, a.eps, a.step, a.step_dev, a.lr_scale_dev);
   __syncthreads();
   const AdamConst c = cs;
   const int64_t total = a.qend[a.n - 1], stride = (int64_t)gridDim.x * blockDim.x;

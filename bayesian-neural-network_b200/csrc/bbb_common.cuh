@@ -290,6 +290,33 @@ __device__ __forceinline__ float logsigma_quad_fast(const float sg[4]) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, no amsgrad, no weight decay).  Shared by the stand-alone multi-tensor kernel
+// (bbb_adam.cu) and by the fused backward, which can apply the update in its gradient epilogue.
+// ---------------------------------------------------------------------------------------
+struct AdamConst {
+  float b1, b2, omb1, omb2, step_size, bc2_sqrt, eps;
+};
+// 1-beta, the bias corrections and the step size are formed in double, as torch does on the host
+__device__ __forceinline__ AdamConst adam_consts(double lr, double b1, double b2, float eps, uint32_t step,
+                                                 const uint32_t *step_dev, const float *lr_scale_dev) {
+  const uint32_t t = step + (step_dev ? *step_dev : 0u);
+  const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+  const double lr_t = lr * (lr_scale_dev ? (double)*lr_scale_dev : 1.0);
+  AdamConst c;
+  c.b1 = (float)b1; c.b2 = (float)b2;
+  c.omb1 = (float)(1.0 - b1); c.omb2 = (float)(1.0 - b2);
+  c.step_size = (float)(lr_t / bc1); c.bc2_sqrt = (float)sqrt(bc2); c.eps = eps;
+  return c;
+}
+// lerp_(g, 1-b1);  mul_(b2).addcmul_(g, g, 1-b2);  denom = sqrt(v)/sqrt(bc2) + eps;  addcdiv_(m, denom, -step_size)
+__device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, const AdamConst &c) {
+  m = fmaf(c.omb1, g - m, m);
+  v = fmaf(c.omb2 * g, g, c.b2 * v);
+  const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
+  p = fmaf(-c.step_size, m / denom, p);
+}
+
+// ---------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -24,6 +24,14 @@ struct LinArgs {
   int64_t g_dev_stride;
   const float *out_scale_dev;
   float *dx, *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;
+  // optional optimiser step fused into the backward (bbb_linear_bwd_adam): state of w_mu, w_rho, b_mu, b_rho
+  bool adam_on;
+  float *adam_m[4], *adam_v[4];
+  double adam_lr, adam_b1, adam_b2;
+  float adam_eps;
+  uint32_t adam_step;
+  const uint32_t *adam_step_dev;
+  const float *adam_lr_scale_dev;
   // derived
   bool vec_in;   // in % 4 == 0 and every [*, in] base pointer 16-byte aligned
   bool vec_out;  // out % 4 == 0 and every [*, out] base pointer 16-byte aligned

@@ -112,11 +112,18 @@ def _ws_fwd(x, x_stride, p, eps, l, prior, S, B, flags, y, logp, logq):
 
 
 def _ws_bwd(dy, mask, x, x_stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev, gq_dev, g_stride, out_scale, dx,
-            grads):
+            grads, adam=None):
     wm, wr, bm, br = p
     out, inn = wm.shape
     ew, eb = eps.ptrs(l)
     rng = eps.rng(l)
+    if adam is not None:      # the optimiser's update is applied inside the kernel; no gradient is written
+        L.check(L.lib().bbb_linear_bwd_adam(L.ptr(dy), L.ptr(mask), L.ptr(x), x_stride, L.ptr(wm), L.ptr(wr),
+                                            L.ptr(bm), L.ptr(br), ew, eb, C.byref(rng), C.byref(prior), S, B, inn,
+                                            out, flags, gp, gq, L.ptr(gp_dev), L.ptr(gq_dev), g_stride,
+                                            L.ptr(out_scale), L.ptr(dx), C.byref(adam), L.stream()),
+                'bbb_linear_bwd_adam')
+        return
     L.check(L.lib().bbb_linear_bwd(L.ptr(dy), L.ptr(mask), L.ptr(x), x_stride, L.ptr(wm), L.ptr(wr), L.ptr(bm),
                                    L.ptr(br), ew, eb, C.byref(rng), C.byref(prior), S, B, inn, out, flags,
                                    gp, gq, L.ptr(gp_dev), L.ptr(gq_dev), g_stride, L.ptr(out_scale), L.ptr(dx),
@@ -151,13 +158,13 @@ def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq
 
 
 def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq, gp_dev, gq_dev, g_stride,
-                     out_scale, need_dx0):
+                     out_scale, need_dx0, fused_opt=None, live_params=None):
     """Backward of _net_ws_forward.  Returns (dx0 or None, [grads per layer]).  Every layer above the first
     hands down the gradient w.r.t. the PRE-activation output of the layer below (BBB_F_DX_PREACT: the ReLU mask
     is applied where dx is produced), so no layer needs a separate mask pass over dy."""
     B = x2.shape[0]
     base = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0) | L.F_OUT_ZEROED
-    grads = _alloc_grads(params)
+    grads = _alloc_grads(params) if fused_opt is None else [None] * len(params)
     dy, dx0 = d_out, None
     first = 0 if need_dx0 else 1
     dxs = [None] * first + _zeroed_views([(S, B, p[0].shape[1]) for p in params[first:]], x2.device)
@@ -173,8 +180,9 @@ def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq,
         if l == 0 and need_dx0:
             flags |= L.F_SCALE_DX
         x_in, stride = (x2, 0) if l == 0 else (ys[l - 1], B * inn)
+        adam = fused_opt.fuse_descriptor(live_params[l]) if fused_opt is not None else None
         _ws_bwd(dy, None, x_in, stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev, gq_dev, g_stride, out_scale,
-                dx, g)
+                dx, g, adam)
         dy = dx
         if l == 0:
             dx0 = dx
@@ -280,7 +288,7 @@ class _FusedELBO(torch.autograd.Function):
     backward is 5 launches.  Only `loss` is differentiable."""
 
     @staticmethod
-    def forward(ctx, x2, target, beta, S, sigma, mode, prior, tf32, *flat):
+    def forward(ctx, x2, target, beta, S, sigma, mode, prior, tf32, fused_opt, *flat):
         L.require_cuda(x2, target, *flat)
         x2 = _f32c(x2)
         dev = x2.device
@@ -308,6 +316,7 @@ class _FusedELBO(torch.autograd.Function):
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *eps.tensors())
         ctx.cfg = (prior, S, beta_h, tf32, eps, len(params))
         ctx.beta_dev = beta_d
+        ctx.fused_opt, ctx.live = fused_opt if fused_opt is not None else (None, None)
         loss, lp, lq, nl = out4[0:1], out4[1], out4[2], out4[3:4]
         ctx.mark_non_differentiable(lp, lq, nl)
         return loss, lp, lq, nl
@@ -321,15 +330,22 @@ class _FusedELBO(torch.autograd.Function):
         ys = list(sv[2 + 4 * nl:2 + 4 * nl + nl - 1]) + [None]
         scale = _f32c(g_loss).reshape(1)
         bd = ctx.beta_dev
+        if ctx.fused_opt is not None:     # Adam rides in the backward kernels: parameters change here, no .grad appears
+            with torch.no_grad():
+                _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S, bd, bd, 0,
+                                 scale, False, ctx.fused_opt, ctx.live)
+            return (None,) * (9 + 4 * nl)
         _, grads = _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S,
                                     bd, bd, 0, scale, False)
         flat = [g for lg in grads for g in lg]
-        return (None,) * 8 + tuple(flat)
+        return (None,) * 9 + tuple(flat)
 
 
-def fused_elbo(x2, target, beta, S, sigma, mode, prior, layers, tf32=False):
+def fused_elbo(x2, target, beta, S, sigma, mode, prior, layers, tf32=False, fused_opt=None):
+    """fused_opt: None, or a bnn_b200.FusedAdam whose next step the backward kernels apply themselves."""
     flat = [t for layer in layers for t in layer]
-    return _FusedELBO.apply(x2, target, beta, S, sigma, mode, prior, tf32, *flat)
+    fo = (fused_opt, [tuple(layer) for layer in layers]) if fused_opt is not None else None
+    return _FusedELBO.apply(x2, target, beta, S, sigma, mode, prior, tf32, fo, *flat)
 
 
 # =========================================================================================

@@ -277,7 +277,9 @@ def kernel_bytes(tag, a, L):
         if tag.endswith(':dgrad'):
             return S * 8 * inn * out + 4 * S * B * out + mask + 4 * S * B * inn
         dx = 0 if (a[16 if tag.startswith('bbb_linear_bwd') else 17] & L.F_NO_DX) else 4 * S * B * inn
-        return S * 8 * inn * out + 8 * inn * out + act + (dx if not tag.endswith(':wgrad') else 0)
+        # gradient write (8 B/weight), or with the fused optimiser: read m, v (16) + write p, m, v (24) for mu and rho
+        tail = 40 if tag.startswith('bbb_linear_bwd_adam') else 8
+        return S * 8 * inn * out + tail * inn * out + act + (dx if not tag.endswith(':wgrad') else 0)
     return None
 
 
@@ -479,7 +481,10 @@ def run_b200(args):
                 steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, steps_per_s=1e3 / ms,
                 higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='tf32' if tf32 else 'f32', data='synthetic',
-                config=dict(workload=workload_name(args.workload, w, S), optimizer='Adam, one fused multi-tensor launch (bnn_b200.FusedAdam, same update rule as torch.optim.Adam)',
+                config=dict(workload=workload_name(args.workload, w, S),
+                            optimizer=('Adam applied in the backward kernels\' gradient epilogue (bbb_linear_bwd_adam; same update rule as torch.optim.Adam)'
+                                       if getattr(graphed, 'optimizer_fused', False) else
+                                       'Adam, one fused multi-tensor launch (bnn_b200.FusedAdam, same update rule as torch.optim.Adam)'),
                             parallelism=f'MC samples sharded over {world} GPU(s), disjoint Philox sample indices'
                                         + (', NCCL all-reduce of the mu/rho gradients' if world > 1 else ''),
                             l2='flushed between timed steps (256 MiB write), flush outside the CUDA-event brackets',

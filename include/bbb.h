@@ -110,6 +110,27 @@ int bbb_linear_bwd(const float *dy, const float *dy_mask_src, const float *x, in
                    const float *out_scale_dev, float *dx, float *grad_w_mu, float *grad_w_rho,
                    float *grad_b_mu, float *grad_b_rho, void *stream);
 
+/* The same backward with the optimiser step fused into its gradient epilogue: once a CTA holds the
+ * complete gradient of its block of weights it applies torch.optim.Adam's update to w_mu / w_rho / b_mu / b_rho in
+ * place and never writes the gradient -- the 16 B/weight gradient round trip and the optimiser launch disappear.
+ * Replaces loss.backward() + optimiser.step() at reg_task.py:72-73, class_task.py:78-79, bandits.py:49-50 for
+ * single-GPU steps (with several GPUs the gradients must be all-reduced first: use bbb_linear_bwd + bbb_adam_step).
+ * Only the fused tcgen05 backward implements it (BBB_F_TF32, B <= 128, rows of 16-byte multiples); otherwise the
+ * call returns BBB_EUNSUPPORTED and nothing is launched.  exp_avg / exp_avg_sq: state of w_mu, w_rho, b_mu, b_rho. */
+typedef struct bbb_adam_fuse {
+  float *exp_avg[4], *exp_avg_sq[4];
+  double lr, beta1, beta2, eps;
+  uint32_t step;              /* 1-based Adam step; *step_dev is added when non-NULL (CUDA-graph replay)       */
+  const uint32_t *step_dev;
+  const float *lr_scale_dev;  /* optional device scalar multiplying lr                                        */
+} bbb_adam_fuse;
+int bbb_linear_bwd_adam(const float *dy, const float *dy_mask_src, const float *x, int64_t x_sample_stride,
+                        float *w_mu, float *w_rho, float *b_mu, float *b_rho, const float *eps_w,
+                        const float *eps_b, const bbb_rng *rng, const bbb_prior *prior, int64_t S, int64_t B,
+                        int64_t in, int64_t out, int32_t flags, float gp, float gq, const float *gp_dev,
+                        const float *gq_dev, int64_t g_dev_stride, const float *out_scale_dev, float *dx,
+                        const bbb_adam_fuse *adam, void *stream);
+
 /* ---- local-reparameterisation layer ----------------------------------------------------
  * replaces BayesianLinearLR.forward (networks.py:116-138) and compute_kl_cost (109-114).
  *   w_mu,w_rho [in,out] (the reference's LR layout, networks.py:95-96)

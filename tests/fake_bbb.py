@@ -126,6 +126,25 @@ class FakeLib:
             G[...] = (G + osc * val if flags & F_ACCUM else osc * val).astype(np.float32)
         return 0
 
+    def bbb_linear_bwd_adam(self, dy, mask, x, xs, wm, wr, bm, br, ew, eb, rng, prior, S, B, inn, out, flags, gp, gq,
+                            gp_dev, gq_dev, gstride, oscale, dx, adam, st):
+        """backward, then the optimiser's update of (w_mu, w_rho, b_mu, b_rho) in place; no gradient output"""
+        assert flags & F_TF32 and not flags & (F_ACCUM | F_NO_WGRAD)
+        d = adam._obj
+        gs = [np.zeros(sh, dtype=np.float32) for sh in ((out, inn), (out, inn), (out,), (out,))]
+        self.bbb_linear_bwd(dy, mask, x, xs, wm, wr, bm, br, ew, eb, rng, prior, S, B, inn, out, flags, gp, gq, gp_dev,
+                            gq_dev, gstride, oscale, dx, *[g.ctypes.data for g in gs], st)
+        self.calls[-1] = 'linear_bwd_adam'
+        t = d.step + (int(_arr(d.step_dev, C.c_uint32, 1)[0]) if d.step_dev else 0)
+        lr = d.lr * (float(_f(d.lr_scale_dev, 1)[0]) if d.lr_scale_dev else 1.0)
+        bc1, bc2 = 1 - d.beta1 ** t, 1 - d.beta2 ** t
+        for k, (ptr, g) in enumerate(zip((wm, wr, bm, br), gs)):
+            p, m, v = _f(ptr, *g.shape), _f(d.exp_avg[k], *g.shape), _f(d.exp_avg_sq[k], *g.shape)
+            m[...] = d.beta1 * m + (1 - d.beta1) * g
+            v[...] = d.beta2 * v + (1 - d.beta2) * g * g
+            p[...] = p - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + d.eps)
+        return 0
+
     # ---------------------------------------------------------------- local reparameterisation
     def bbb_lr_linear_fwd(self, x, xs, wm, wr, bm, br, ea, eb, rng, sigma_p, S, B, inn, out, flags, y, delta, kl, st):
         self.calls.append('lr_fwd')

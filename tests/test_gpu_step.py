@@ -76,3 +76,30 @@ def test_graphed_step_equals_eager_steps(name, tf32):
             assert bad.float().mean() <= 0.03, float(bad.float().mean())
             assert float((p - q).abs().max()) <= 3 * 2 * 1e-3 * 1.05
     assert losses_g[0] != losses_g[1]                   # fresh eps every replay
+
+
+def test_fused_optimizer_matches_separate_adam_on_gpu():
+    """bbb_linear_bwd_adam (Adam in the backward epilogue) == bbb_linear_bwd + bbb_adam_step, same Philox draws.
+    One step, so the comparison is not blurred by the TF32 path's run-to-run reorder noise feeding Adam's sign."""
+    c = Case('cfg2_mnist_mix')
+    x, y = c.x.to(DEV), c.y.to(DEV)
+    res = []
+    for fuse in (False, True):
+        net = PC.build_net(c, DEV, tf32=True).train()
+        opt = bnn_b200.FusedAdam(net.parameters(), lr=1e-3)
+        if fuse:
+            assert net.fuse_optimizer(opt)
+        bnn_b200.manual_seed(77, 5)
+        net.zero_grad()
+        net.sample_elbo(x, y, c.beta, c.S)[0].backward()
+        assert all((p.grad is None) == fuse for p in net.parameters())
+        opt.step()
+        res.append(([p.detach().clone() for p in net.parameters()],
+                    [opt.state[p]['exp_avg_sq'].clone() for p in net.parameters()]))
+    for a, b in zip(res[0][0], res[1][0]):
+        bad = ~torch.isclose(a, b, rtol=1e-5, atol=1e-7)
+        assert bad.float().mean() <= 1e-3, float(bad.float().mean())      # sign flips of round-off-sized gradients
+        assert float((a - b).abs().max()) <= 2 * 1e-3 * 1.01
+    for a, b in zip(res[0][1], res[1][1]):
+        bad = ~torch.isclose(a, b, rtol=1e-2, atol=1e-10)                   # v = (1-b2) g^2: the gradients agree
+        assert bad.float().mean() <= 1e-3, float(bad.float().mean())

@@ -125,3 +125,35 @@ def test_beta_may_be_a_tensor(fake):
         info[0].backward()
         outs.append((float(info[0].detach()), net.l2.weight_rho.grad.clone()))
     assert outs[0][0] == outs[1][0] and torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-9)
+
+
+def test_fused_optimizer_step_equals_backward_then_adam(fake):
+    """net.fuse_optimizer(opt): backward applies Adam inside bbb_linear_bwd_adam and leaves .grad unset; the
+    parameters after 2 steps equal backward + FusedAdam.step()."""
+    c = Case('small_cls_mix')
+    res = []
+    for fuse in (False, True):
+        net = PC.build_net(c, 'cpu', tf32=True).train()
+        opt = bnn_b200.FusedAdam(net.parameters(), lr=1e-2)
+        if fuse:
+            assert net.fuse_optimizer(opt)
+        with bnn_b200.eps_mode('reference'):
+            torch.manual_seed(5)
+            for _ in range(2):
+                net.zero_grad()
+                loss = net.sample_elbo(c.x, c.y, c.beta, c.S)[0]
+                loss.backward()
+                assert all((p.grad is None) == fuse for p in net.parameters())
+                opt.step()
+        res.append([p.detach().clone() for p in net.parameters()])
+        assert ('linear_bwd_adam' in fake.calls) == fuse
+    for a, b in zip(*res):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), float((a - b).abs().max())
+
+
+def test_fuse_optimizer_refuses_what_the_kernel_cannot_do(fake):
+    c = Case('small_reg_mix')                      # input width 5: rows are not 16-byte multiples
+    net = PC.build_net(c, 'cpu', tf32=True)
+    assert net.fuse_optimizer(bnn_b200.FusedAdam(net.parameters())) is False and net._fused_opt is None
+    net = PC.build_net(Case('small_lr_cls'), 'cpu')
+    assert net.fuse_optimizer(bnn_b200.FusedAdam(net.parameters())) is False
