@@ -36,6 +36,12 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+# Called as hook(layer_index, flat_gradient_slice) right after a layer's backward kernel has been launched (from the
+# thread autograd runs the backward on).  parallel.OverlappedAllReduce installs it so that a layer's mu/rho gradients
+# travel over NVLink while the layers below are still being differentiated.
+grad_ready_hook = None
+
+
 def _alloc_grads(params):
     """Gradient buffers for every layer as consecutive views of ONE flat tensor, in parameter order, so a
     multi-GPU step can all-reduce them with a single collective and no copies (parallel.py)."""
@@ -43,12 +49,21 @@ def _alloc_grads(params):
     flat = torch.empty(total, dtype=torch.float32, device=params[0][0].device)
     out, off = [], 0
     for p in params:
-        g = []
+        g, start = [], off
         for t in p:
             g.append(flat[off:off + t.numel()].view(t.shape))
             off += t.numel()
-        out.append(tuple(g))
+        out.append(_LayerGrads(g, flat[start:off]))
     return out
+
+
+class _LayerGrads(tuple):
+    """(grad_w_mu, grad_w_rho, grad_b_mu, grad_b_rho) of one layer + the flat slice of the bucket they live in"""
+
+    def __new__(cls, grads, flat):
+        self = super().__new__(cls, grads)
+        self.flat = flat
+        return self
 
 
 def _split_beta(beta):
@@ -183,6 +198,8 @@ def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq,
         adam = fused_opt.fuse_descriptor(live_params[l]) if fused_opt is not None else None
         _ws_bwd(dy, None, x_in, stride, p, eps, l, prior, S, B, flags, gp, gq, gp_dev, gq_dev, g_stride, out_scale,
                 dx, g, adam)
+        if grad_ready_hook is not None and fused_opt is None:
+            grad_ready_hook(l, g.flat)
         dy = dx
         if l == 0:
             dx0 = dx

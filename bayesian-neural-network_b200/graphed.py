@@ -25,6 +25,7 @@ class GraphedTrainStep:
         self.beta = torch.full((1,), float(beta), dtype=torch.float32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)      # read as uint32 by the kernels
         self._elbo = net.sample_elbo_lr if net.local_reparam else net.sample_elbo
+        self._ar = parallel.OverlappedAllReduce(world_size)
         if hasattr(optimizer, 'use_device_step'):
             optimizer.use_device_step(self.counter)
         # Opt-in, one GPU: the optimiser's update rides in the backward kernels' gradient epilogue (no gradient round
@@ -66,10 +67,10 @@ class GraphedTrainStep:
 
     def _step(self):
         self.net.zero_grad(set_to_none=True)
-        info = self._elbo(self.x, self.y, self.beta, self.samples, sigma=self.sigma)
-        info[0].backward()
-        if self.world > 1:
-            parallel.allreduce_gradients(self.net, self.world)
+        with self._ar:
+            info = self._elbo(self.x, self.y, self.beta, self.samples, sigma=self.sigma)
+            info[0].backward()
+        self._ar.join(self.net)
         self.opt.step()
         L.check(L.lib().bbb_counter_add(self.counter.data_ptr(), 1, L.stream()), 'bbb_counter_add')
         return info

@@ -50,6 +50,68 @@ def allreduce_gradients(module, world_size=None, group=None):
             off += g.numel()
 
 
+class OverlappedAllReduce:
+    """Per-layer gradient all-reduce on a side stream, overlapped with the rest of the backward.
+
+        with parallel.OverlappedAllReduce(world_size) as ar:
+            loss = net.sample_elbo(...)[0]
+            loss.backward()             # layer l's bucket slice is all-reduced while layers < l are differentiated
+        ar.join()                       # the current stream waits for the collectives
+        optimizer.step()
+
+    Works under CUDA-graph capture (the fork/join become graph edges).  Only the network-level weight-sampling
+    backward reports its layers (functional.grad_ready_hook); anything it does not cover is reduced by join()."""
+
+    def __init__(self, world_size=None, group=None):
+        self.world = world_size or dist.get_world_size(group)
+        self.group = group
+        self.stream = None
+        self.reduced = 0
+
+    def __enter__(self):
+        from . import functional as F
+        self.reduced = 0
+        if self.world > 1:
+            F.grad_ready_hook = self._on_layer
+        return self
+
+    def __exit__(self, *exc):
+        from . import functional as F
+        F.grad_ready_hook = None
+
+    def _reduce(self, flat):
+        if dist.get_backend(self.group) == 'nccl':
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+
+    def _on_layer(self, layer, flat):
+        self.reduced += 1
+        if not flat.is_cuda:                            # CPU tests (gloo): nothing to overlap with
+            self._reduce(flat)
+            return
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)                    # the layer's backward kernel has been launched on `cur`
+        with torch.cuda.stream(self.stream):
+            self._reduce(flat)
+        flat.record_stream(self.stream)
+
+    def join(self, module=None):
+        """Make the current stream wait for the collectives; if no layer reported (other estimators / layer-level
+        API), fall back to one all-reduce over the whole bucket."""
+        if self.world <= 1:
+            return
+        if self.reduced == 0:
+            if module is not None:
+                allreduce_gradients(module, self.world, self.group)
+            return
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
 def allreduce_scalars(values, world_size=None, group=None):
     """Average the ELBO scalars (loss, log prior, log posterior, NLL) over the ranks."""
     world_size = world_size or dist.get_world_size(group)

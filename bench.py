@@ -326,12 +326,18 @@ def run_b200(args):
     loss_h = torch.empty(1, pin_memory=True)
     elbo = net.sample_elbo_lr if w['lrp'] else net.sample_elbo
 
+    ar = parallel.OverlappedAllReduce(world)
+
     def step(x, y, collective=True):
         net.zero_grad()
-        loss = elbo(x, y, beta, S, sigma=sigma)[0]
-        loss.backward()
         if world > 1 and collective:
-            parallel.allreduce_gradients(net, world)
+            with ar:                                  # per-layer all-reduce overlapped with the backward
+                loss = elbo(x, y, beta, S, sigma=sigma)[0]
+                loss.backward()
+            ar.join(net)
+        else:
+            loss = elbo(x, y, beta, S, sigma=sigma)[0]
+            loss.backward()
         opt.step()
         return loss
 
@@ -486,7 +492,7 @@ def run_b200(args):
                                        if getattr(graphed, 'optimizer_fused', False) else
                                        'Adam, one fused multi-tensor launch (bnn_b200.FusedAdam, same update rule as torch.optim.Adam)'),
                             parallelism=f'MC samples sharded over {world} GPU(s), disjoint Philox sample indices'
-                                        + (', NCCL all-reduce of the mu/rho gradients' if world > 1 else ''),
+                                        + (', per-layer NCCL all-reduce of the mu/rho gradients overlapped with the backward' if world > 1 else ''),
                             l2='flushed between timed steps (256 MiB write), flush outside the CUDA-event brackets',
                             step=graph_note, launches_per_step=launches_per_step,
                             eager_api_ms_per_step=eager_ms,

@@ -47,10 +47,16 @@ def _worker(rank, world, port, out_path):
         fake_bbb.install(_Patch())
         case = Case(CASE)
         first, count = parallel.shard_samples(S_TOTAL, rank, world)
-        net, info = _run(case, _all_eps(case)[first:first + count], count)
-        grads = [p.grad for p in net.parameters()]
-        assert parallel._flat_view_of(grads) is not None        # zero-copy bucket
-        parallel.allreduce_gradients(net, world)
+        if os.environ.get('BBB_TEST_OVERLAP') == '1':            # per-layer all-reduce issued from the backward itself
+            with parallel.OverlappedAllReduce(world) as ar:
+                net, info = _run(case, _all_eps(case)[first:first + count], count)
+            assert ar.reduced == len(case.dims) - 1
+            ar.join(net)
+        else:
+            net, info = _run(case, _all_eps(case)[first:first + count], count)
+            grads = [p.grad for p in net.parameters()]
+            assert parallel._flat_view_of(grads) is not None        # zero-copy bucket
+            parallel.allreduce_gradients(net, world)
         scal = parallel.allreduce_scalars(info, world)
         if rank == 0:
             torch.save(dict(grads=PC.net_grads(net), scal=scal), out_path)
@@ -58,7 +64,11 @@ def _worker(rank, world, port, out_path):
         dist.destroy_process_group()
 
 
-def test_two_rank_sample_sharding_matches_single_process(monkeypatch):
+@pytest.mark.parametrize('overlap', ['0', '1'])
+def test_two_rank_sample_sharding_matches_single_process(monkeypatch, overlap):
+    """overlap=0: one all-reduce over the flat bucket after the backward; overlap=1: OverlappedAllReduce, the
+    per-layer collectives issued from inside the backward.  Both must reproduce the one-process gradients."""
+    monkeypatch.setenv('BBB_TEST_OVERLAP', overlap)
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
