@@ -40,6 +40,7 @@ extern "C" int bbb_linear_fwd(const float *x, int64_t x_sample_stride, const flo
   cudaStream_t st = (cudaStream_t)stream;
   if ((flags & BBB_F_TF32) && linear_sk_supported(a)) return launch_linear_fwd_sk(a, st);
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_fwd_tc(a, st);
+  if (linear_narrow_supported(a)) return launch_linear_fwd_narrow(a, st);   // exact-fp32 mode, out <= 16
   return launch_linear_fwd_fma(a, st);
 }
 
@@ -93,6 +94,7 @@ int linear_bwd_impl(const float *dy, const float *dy_mask_src, const float *x, i
   }
   if ((flags & BBB_F_TF32) && a.S > 0 && linear_bwd_fused_supported(a)) return launch_linear_bwd_fused(a, st);
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_bwd_tc(a, st);
+  if (a.S > 0 && linear_narrow_supported(a)) return launch_linear_bwd_narrow(a, st);   // exact-fp32 mode, out <= 16
   return launch_linear_bwd_fma(a, st);
 }
 }  // namespace

@@ -70,6 +70,11 @@ int launch_linear_bwd_tc(const LinArgs &a, cudaStream_t st);
 bool linear_sk_supported(const LinArgs &a);
 int launch_linear_fwd_sk(const LinArgs &a, cudaStream_t st);
 
+// narrow-output layers (out <= 16: classification / regression heads), exact fp32, both modes (bbb_linear_narrow.cu)
+bool linear_narrow_supported(const LinArgs &a);
+int launch_linear_fwd_narrow(const LinArgs &a, cudaStream_t st);
+int launch_linear_bwd_narrow(const LinArgs &a, cudaStream_t st);
+
 // fused backward (wgrad + analytic epilogue + dgrad, one eps regeneration) for batches of at most 128 rows
 // (bbb_linear_bwd_fused.cu)
 bool linear_bwd_fused_supported(const LinArgs &a);

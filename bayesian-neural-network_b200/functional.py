@@ -150,20 +150,23 @@ def _zeroed_views(shapes, device):
     """One zero-filled buffer carved into tensors of the given shapes (a single memset for all of them): the
     split-K tensor-core kernels add partial tiles into their output with red.add (BBB_F_OUT_ZEROED)."""
     sizes = [int(torch.Size(sh).numel()) for sh in shapes]
-    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+    padded = [(n + 63) // 64 * 64 for n in sizes]           # every view starts on a 256-byte boundary
+    flat = torch.zeros(sum(padded), dtype=torch.float32, device=device)
     out, off = [], 0
-    for sh, n in zip(shapes, sizes):
+    for sh, n, m in zip(shapes, sizes, padded):
         out.append(flat[off:off + n].view(sh))
-        off += n
+        off += m
     return out
 
 
-def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq):
-    """All layers, all S samples.  Returns the list of pre-activation outputs ys[l] = [S,B,out_l]."""
+def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq, ys=None):
+    """All layers, all S samples.  Returns the list of pre-activation outputs ys[l] = [S,B,out_l]
+    (written into the zero-filled `ys` when the caller supplies them)."""
     B = x2.shape[0]
     base = ((L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if logprob else 0) | (L.F_TF32 if tf32 else 0) |
             L.F_OUT_ZEROED)
-    ys = _zeroed_views([(S, B, p[0].shape[0]) for p in params], x2.device)
+    if ys is None:
+        ys = _zeroed_views([(S, B, p[0].shape[0]) for p in params], x2.device)
     inp, stride = x2, 0
     for l, p in enumerate(params):
         out, inn = p[0].shape
@@ -173,7 +176,7 @@ def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq
 
 
 def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq, gp_dev, gq_dev, g_stride,
-                     out_scale, need_dx0, fused_opt=None, live_params=None):
+                     out_scale, need_dx0, fused_opt=None, live_params=None, dxs=None):
     """Backward of _net_ws_forward.  Returns (dx0 or None, [grads per layer]).  Every layer above the first
     hands down the gradient w.r.t. the PRE-activation output of the layer below (BBB_F_DX_PREACT: the ReLU mask
     is applied where dx is produced), so no layer needs a separate mask pass over dy."""
@@ -182,7 +185,8 @@ def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq,
     grads = _alloc_grads(params) if fused_opt is None else [None] * len(params)
     dy, dx0 = d_out, None
     first = 0 if need_dx0 else 1
-    dxs = [None] * first + _zeroed_views([(S, B, p[0].shape[1]) for p in params[first:]], x2.device)
+    if dxs is None:
+        dxs = [None] * first + _zeroed_views([(S, B, p[0].shape[1]) for p in params[first:]], x2.device)
     for l in reversed(range(len(params))):
         p = params[l]
         out, inn = p[0].shape
@@ -311,12 +315,20 @@ class _FusedELBO(torch.autograd.Function):
         dev = x2.device
         params = [tuple(_f32c(t) for t in flat[i:i + 4]) for i in range(0, len(flat), 4)]
         eps = plan_eps([(tuple(p[0].shape), (p[0].shape[0],)) for p in params], S, dev, True)
-        acc = torch.zeros(2 * S + 1, dtype=torch.float64, device=dev)
-        logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
-        ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq)
-        out = ys[-1]
-        B, Cc = out.shape[1], out.shape[2]
         need_grad = any(t.requires_grad for t in flat)
+        B = x2.shape[0]
+        # ONE zero-filled workspace (one memset per step): fp64 accumulators | activations of every layer | dx of
+        # every layer above the first (the backward's split-K kernels add into them)
+        shapes = [(2 * (2 * S + 1),)] + [(S, B, p[0].shape[0]) for p in params]
+        if need_grad:
+            shapes += [(S, B, p[0].shape[1]) for p in params[1:]]
+        ws = _zeroed_views(shapes, dev)
+        acc = ws[0].view(torch.float64)
+        ys, dxs = ws[1:1 + len(params)], ([None] + ws[1 + len(params):] if need_grad else None)
+        logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
+        ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq, ys)
+        out = ys[-1]
+        Cc = out.shape[2]
         d_out = torch.empty_like(out) if need_grad else None
         if mode == 'classification':
             L.check(L.lib().bbb_nll_ce(L.ptr(out), L.ptr(target), S, B, Cc, 1.0 / S, L.ptr(nll), L.ptr(d_out),
@@ -331,6 +343,7 @@ class _FusedELBO(torch.autograd.Function):
                                           L.ptr(out4), L.stream()), 'bbb_elbo_finalize')
         if need_grad:
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *eps.tensors())
+            ctx.dxs = dxs
         ctx.cfg = (prior, S, beta_h, tf32, eps, len(params))
         ctx.beta_dev = beta_d
         ctx.fused_opt, ctx.live = fused_opt if fused_opt is not None else (None, None)
@@ -350,10 +363,10 @@ class _FusedELBO(torch.autograd.Function):
         if ctx.fused_opt is not None:     # Adam rides in the backward kernels: parameters change here, no .grad appears
             with torch.no_grad():
                 _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S, bd, bd, 0,
-                                 scale, False, ctx.fused_opt, ctx.live)
+                                 scale, False, ctx.fused_opt, ctx.live, ctx.dxs)
             return (None,) * (9 + 4 * nl)
         _, grads = _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S,
-                                    bd, bd, 0, scale, False)
+                                    bd, bd, 0, scale, False, dxs=ctx.dxs)
         flat = [g for lg in grads for g in lg]
         return (None,) * 9 + tuple(flat)
 
