@@ -144,6 +144,8 @@ extern "C" int bbb_lr_linear_fwd(const float *x, int64_t x_sample_stride, const 
   a.y = y; a.delta = delta; a.kl = kl;
   a.vec_in = (in % 4 == 0) && all16({x});
   a.vec_out = (out % 4 == 0) && all16({w_mu, w_rho, eps_a, y, delta});
+  if ((flags & BBB_F_TF32) && lr_tc_supported(a)) return launch_lr_fwd_tc(a, (cudaStream_t)stream);
+  if (lr_narrow_supported(a)) return launch_lr_fwd_narrow(a, (cudaStream_t)stream);   // heads: out <= 16, exact fp32
   return launch_lr_fwd_fma(a, (cudaStream_t)stream);
 }
 
@@ -175,5 +177,7 @@ extern "C" int bbb_lr_linear_bwd(const float *dy, const float *dy_mask_src, cons
   a.dx = dx; a.g_w_mu = grad_w_mu; a.g_w_rho = grad_w_rho; a.g_b_mu = grad_b_mu; a.g_b_rho = grad_b_rho;
   a.vec_in = (in % 4 == 0) && all16({x});
   a.vec_out = (out % 4 == 0) && all16({w_mu, w_rho, eps_a, dy, dy_mask_src, delta});
+  if ((flags & BBB_F_TF32) && lr_bwd_tc_supported(a)) return launch_lr_bwd_tc(a, (cudaStream_t)stream);
+  if (a.S > 0 && a.B > 0 && lr_narrow_supported(a)) return launch_lr_bwd_narrow(a, (cudaStream_t)stream);
   return launch_lr_bwd_fma(a, (cudaStream_t)stream);
 }

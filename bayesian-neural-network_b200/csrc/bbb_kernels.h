@@ -61,6 +61,12 @@ int launch_linear_bwd_fma(const LinArgs &a, cudaStream_t st);
 int launch_lr_fwd_fma(const LrArgs &a, cudaStream_t st);
 int launch_lr_bwd_fma(const LrArgs &a, cudaStream_t st);
 
+// local reparameterisation on tcgen05 kind::tf32, batch <= 128 (bbb_lr_tc.cu)
+bool lr_tc_supported(const LrArgs &a);
+int launch_lr_fwd_tc(const LrArgs &a, cudaStream_t st);
+bool lr_bwd_tc_supported(const LrArgs &a);
+int launch_lr_bwd_tc(const LrArgs &a, cudaStream_t st);   // overwrites the forward's delta with dV
+
 // tcgen05 kind::tf32 path (bbb_linear_tc.cu); returns BBB_EUNSUPPORTED when the shape does not fit.
 bool linear_tc_supported(const LinArgs &a);
 int launch_linear_fwd_tc(const LinArgs &a, cudaStream_t st);
@@ -74,6 +80,9 @@ int launch_linear_fwd_sk(const LinArgs &a, cudaStream_t st);
 bool linear_narrow_supported(const LinArgs &a);
 int launch_linear_fwd_narrow(const LinArgs &a, cudaStream_t st);
 int launch_linear_bwd_narrow(const LinArgs &a, cudaStream_t st);
+bool lr_narrow_supported(const LrArgs &a);
+int launch_lr_fwd_narrow(const LrArgs &a, cudaStream_t st);
+int launch_lr_bwd_narrow(const LrArgs &a, cudaStream_t st);
 
 // fused backward (wgrad + analytic epilogue + dgrad, one eps regeneration) for batches of at most 128 rows
 // (bbb_linear_bwd_fused.cu)

@@ -240,6 +240,212 @@ __global__ void __launch_bounds__(NTH) narrow_bwd_kernel(const LinArgs a_in, int
   }
 }
 
+// ==================================================================================================
+// local-reparameterisation layer with a narrow output (weights [in, out], out <= 16), exact fp32
+// ==================================================================================================
+__device__ __forceinline__ float lr_eps_a(const LrArgs &a, int s, int64_t idx) {   // idx = b * out + o
+  if (a.eps_a) return __ldg(a.eps_a + (int64_t)s * a.B * a.out + idx);
+  if (a.vec_out) {                        // same coordinates as the quad-wise generators of the other LR kernels
+    float e[4];
+    philox_normal4(a.rng, a.rng.tensor_w, a.rng.sample_base + (uint32_t)s, (uint32_t)(idx >> 2), e);
+    return e[idx & 3];
+  }
+  return philox_normal1(a.rng, a.rng.tensor_w, a.rng.sample_base + (uint32_t)s, (uint64_t)idx);
+}
+__device__ __forceinline__ float lr_eps_b(const LrArgs &a, int s, int64_t o) {
+  return a.eps_b ? __ldg(a.eps_b + (int64_t)s * a.out + o)
+                 : philox_normal1(a.rng, a.rng.tensor_b, a.rng.sample_base + (uint32_t)s, (uint64_t)o);
+}
+__device__ __forceinline__ float lr_kl_elem(float mu, float sg, float log_sp, float inv_sp2) {
+  return 0.5f * (2.0f * (log_sp - logf(sg)) - 1.0f + (sg * sg + mu * mu) * inv_sp2);
+}
+
+// forward: grid (row groups, S); mu and sigma^2 of the whole layer in shared memory, one warp per batch row
+constexpr int LNT = 1024;   // threads of the LR narrow forward: the layer's weights are staged once per CTA
+__global__ void __launch_bounds__(LNT) lr_narrow_fwd_kernel(const LrArgs a_in, int rows_per_cta) {
+  extern __shared__ __align__(16) float Wm[];   // [in][out] mu, then [in][out] sigma^2
+  __shared__ float bias_s[NO];
+  __shared__ float red[64];
+  pdl_launch_dependents();
+  pdl_wait();
+  LrArgs a = a_in;
+  rng_resolve(a.rng);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, s = blockIdx.y;
+  const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN;
+  const bool klcta = (a.flags & BBB_F_LOGPROB) && blockIdx.x == 0 && s == 0;
+  const int in = (int)a.in, out = (int)a.out, nw = in * out;
+  float *Wv = Wm + nw;
+  const float log_sp = logf(a.sigma_p), inv_sp2 = 1.0f / (a.sigma_p * a.sigma_p);
+  float kl = 0.0f;
+  for (int e = tid; e < nw; e += LNT) {
+    const float mu = __ldg(a.w_mu + e);
+    Wm[e] = mu;
+    if (sample || klcta) {
+      const float sg = softplus_f(__ldg(a.w_rho + e));
+      Wv[e] = sg * sg;
+      if (klcta) kl += lr_kl_elem(mu, sg, log_sp, inv_sp2);
+    }
+  }
+  if (tid < out) {
+    const float mu = __ldg(a.b_mu + tid);
+    float bv = mu;
+    if (sample || klcta) {
+      const float sg = softplus_f(__ldg(a.b_rho + tid));
+      if (sample) bv = fmaf(sg, lr_eps_b(a, s, tid), mu);
+      if (klcta) kl += lr_kl_elem(mu, sg, log_sp, inv_sp2);
+    }
+    bias_s[tid] = bv;
+  }
+  __syncthreads();
+  const int64_t r_end = min(a.B, (int64_t)(blockIdx.x + 1) * rows_per_cta);
+  const float *xs = a.x + (int64_t)s * a.x_sstride;
+  const int64_t base = (int64_t)s * a.B * a.out;
+  for (int64_t b = (int64_t)blockIdx.x * rows_per_cta + warp; b < r_end; b += LNT / 32) {
+    float g[NO], v[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) g[o] = v[o] = 0.0f;
+    for (int k0 = lane; k0 < in; k0 += 128) {
+      float xq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                     // four independent loads in flight
+        const int k = k0 + 32 * u;
+        const float x = k < in ? __ldg(xs + b * a.in + k) : 0.0f;
+        xq[u] = relu ? fmaxf(x, 0.0f) : x;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u;
+        if (k < in) {
+          const float x = xq[u], x2 = x * x;
+#pragma unroll
+          for (int o = 0; o < NO; ++o) {
+            if (o < out) {
+              g[o] = fmaf(x, Wm[k * out + o], g[o]);
+              if (sample) v[o] = fmaf(x2, Wv[k * out + o], v[o]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      if (o < out) {
+        const float gs = warp_sum(g[o]), vs = sample ? warp_sum(v[o]) : 0.0f;
+        if (lane == o) {
+          const float d = sample ? sqrtf(vs) : 0.0f;
+          const float e = sample ? lr_eps_a(a, s, b * a.out + o) : 0.0f;
+          a.y[base + b * a.out + o] = gs + d * e + bias_s[o];
+          if (a.delta) a.delta[base + b * a.out + o] = d;
+        }
+      }
+    }
+  }
+  if (klcta) block_sum2_atomic(kl, 0.0f, red, a.kl, nullptr);
+}
+
+// backward: grid over ranges of <= 32 weight rows (input features); a CTA owns mu/rho[i_lo:i_hi, :] completely
+__global__ void __launch_bounds__(NTH) lr_narrow_bwd_kernel(const LrArgs a_in, int wrows) {
+  __shared__ float dz_s[BC][NO], dv_s[BC][NO];
+  __shared__ float x_s[BC][32 + 1];
+  __shared__ float Mu[32][NO], S2[32][NO];   // this CTA's rows of mu and sigma^2
+  pdl_launch_dependents();
+  pdl_wait();
+  LrArgs a = a_in;
+  rng_resolve(a.rng);
+  const int tid = threadIdx.x;
+  const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN, wgrad = !(a.flags & BBB_F_NO_WGRAD);
+  const bool want_dx = !(a.flags & BBB_F_NO_DX), dx_preact = a.flags & BBB_F_DX_PREACT, accum = a.flags & BBB_F_ACCUM;
+  const int out = (int)a.out;
+  const int64_t i_lo = (int64_t)blockIdx.x * wrows;
+  const int w = (int)min((int64_t)wrows, a.in - i_lo);
+  const bool bias_cta = blockIdx.x == 0;
+  const float osc = a.out_scale_dev ? __ldg(a.out_scale_dev) : 1.0f;
+  const float dxs = ((a.flags & BBB_F_SCALE_DX) && a.out_scale_dev) ? osc : 1.0f;
+  const float gk = (a.flags & BBB_F_LOGPROB) ? a.g_kl * (a.g_kl_dev ? __ldg(a.g_kl_dev) : 1.0f) : 0.0f;
+  const float inv_sp2 = 1.0f / (a.sigma_p * a.sigma_p);
+  // weight thread t < w * out owns element (i_lo + t / out, t % out)
+  const bool wthread = tid < w * out;
+  const int wi = wthread ? tid / out : 0, wo = wthread ? tid - wi * out : 0;
+  const int64_t we = (i_lo + wi) * a.out + wo;
+  float mu = 0.0f, sg = 1.0f;
+  if (wthread) {
+    mu = __ldg(a.w_mu + we);
+    sg = softplus_f(__ldg(a.w_rho + we));
+    Mu[wi][wo] = mu;
+    S2[wi][wo] = sg * sg;
+  }
+  float g1 = 0.0f, g2 = 0.0f, gbmu = 0.0f, gbrho = 0.0f;
+  for (int s = 0; s < a.S; ++s) {
+    const int64_t base = (int64_t)s * a.B * a.out;
+    const float *xs = a.x + (int64_t)s * a.x_sstride;
+    float colsum = 0.0f;
+    for (int64_t b0 = 0; b0 < a.B; b0 += BC) {
+      const int nb = (int)min((int64_t)BC, a.B - b0);
+      __syncthreads();
+      for (int idx = tid; idx < nb * out; idx += NTH) {
+        const int b = idx / out, o = idx - b * out;
+        const int64_t e = (b0 + b) * a.out + o;
+        float z = __ldg(a.dy + base + e);
+        if (a.mask && !(__ldg(a.mask + base + e) > 0.0f)) z = 0.0f;
+        float dv = 0.0f;
+        if (sample) {
+          const float d = __ldg(a.delta_in + base + e);
+          if (d > 0.0f) dv = z * lr_eps_a(a, s, e) / (2.0f * d);
+        }
+        dz_s[b][o] = z;
+        dv_s[b][o] = dv;
+      }
+      for (int idx = tid; idx < nb * w; idx += NTH) {
+        const int b = idx / w, i = idx - b * w;
+        float x = __ldg(xs + (b0 + b) * a.in + i_lo + i);
+        x_s[b][i] = relu ? fmaxf(x, 0.0f) : x;
+      }
+      __syncthreads();
+      if (wgrad && wthread) {
+        for (int b = 0; b < nb; ++b) {
+          const float x = x_s[b][wi];
+          g1 = fmaf(x, dz_s[b][wo], g1);
+          g2 = fmaf(x * x, dv_s[b][wo], g2);
+        }
+      }
+      if (wgrad && bias_cta && tid < out)
+        for (int b = 0; b < nb; ++b) colsum += dz_s[b][tid];
+      if (want_dx) {
+        float *dxr = a.dx + (int64_t)s * a.B * a.in + i_lo;
+        for (int idx = tid; idx < nb * w; idx += NTH) {
+          const int b = idx / w, i = idx - b * w;
+          float p1 = 0.0f, p2 = 0.0f;
+          for (int o = 0; o < out; ++o) {
+            p1 = fmaf(dz_s[b][o], Mu[i][o], p1);
+            p2 = fmaf(dv_s[b][o], S2[i][o], p2);
+          }
+          const float x = x_s[b][i];
+          float d = dxs * fmaf(2.0f * x, p2, p1);
+          if (dx_preact && !(x > 0.0f)) d = 0.0f;
+          dxr[(b0 + b) * a.in + i] = d;
+        }
+      }
+    }
+    if (wgrad && bias_cta && tid < out) {
+      gbmu += colsum;
+      if (sample) gbrho += colsum * lr_eps_b(a, s, tid);
+    }
+  }
+  if (wgrad && wthread) {
+    const float gm = fmaf(gk * mu, inv_sp2, g1);
+    const float gr = -expm1f(-sg) * (2.0f * sg * g2 + gk * (sg * inv_sp2 - 1.0f / sg));
+    a.g_w_mu[we] = accum ? fmaf(osc, gm, a.g_w_mu[we]) : osc * gm;
+    a.g_w_rho[we] = accum ? fmaf(osc, gr, a.g_w_rho[we]) : osc * gr;
+  }
+  if (wgrad && bias_cta && tid < out) {
+    const float bmu = a.b_mu[tid], bsg = softplus_f(a.b_rho[tid]);
+    const float gm = fmaf(gk * bmu, inv_sp2, gbmu);
+    const float gr = -expm1f(-bsg) * (gbrho + gk * (bsg * inv_sp2 - 1.0f / bsg));
+    a.g_b_mu[tid] = accum ? fmaf(osc, gm, a.g_b_mu[tid]) : osc * gm;
+    a.g_b_rho[tid] = accum ? fmaf(osc, gr, a.g_b_rho[tid]) : osc * gr;
+  }
+}
+
 inline int cdiv_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 constexpr int kMaxWsBytes = 200 * 1024;
 
@@ -273,6 +479,32 @@ int launch_linear_bwd_narrow(const LinArgs &a, cudaStream_t st) {
   if (wq > 8) wq = 8;
   if (wq < 1) wq = 1;
   BBB_CHECK_CUDA(launch_pdl(narrow_bwd_kernel, dim3(cdiv_i(nq_i, wq)), dim3(NTH), 0, st, a, wq));
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+bool lr_narrow_supported(const LrArgs &a) {
+  return a.out >= 1 && a.out <= NO && a.in >= 1 && a.B >= 1 && a.S >= 1 &&
+         2 * a.in * a.out * (int64_t)sizeof(float) <= kMaxWsBytes;
+}
+
+int launch_lr_fwd_narrow(const LrArgs &a, cudaStream_t st) {
+  int rows = cdiv_i(a.B * a.S, 2 * kSMs);
+  rows = ((rows < 64 ? 64 : rows) + 31) / 32 * 32;      // >= 2 rows per warp: the weight staging is per CTA
+  dim3 grid(cdiv_i(a.B, rows), (unsigned)a.S);
+  const size_t smem = 2 * (size_t)a.in * a.out * sizeof(float);
+  BBB_CHECK_CUDA(cudaFuncSetAttribute(lr_narrow_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxWsBytes));
+  BBB_CHECK_CUDA(launch_pdl(lr_narrow_fwd_kernel, grid, dim3(LNT), smem, st, a, rows));
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+int launch_lr_bwd_narrow(const LrArgs &a, cudaStream_t st) {
+  int wrows = cdiv_i(a.in, kSMs);        // about one range of weight rows per SM
+  const int cap = NTH / (int)a.out < 32 ? NTH / (int)a.out : 32;   // one thread per owned weight
+  if (wrows > cap) wrows = cap;
+  if (wrows < 1) wrows = 1;
+  BBB_CHECK_CUDA(launch_pdl(lr_narrow_bwd_kernel, dim3(cdiv_i(a.in, wrows)), dim3(NTH), 0, st, a, wrows));
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }

@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(NT) lr_dgrad_kernel(const LrArgs a_in) {
       if (c + j < a.in) {
         float xv = xs[b * a.in + c + j];
         if (relu) xv = fmaxf(xv, 0.0f);
-        dxs[b * a.in + c + j] = dsc * fmaf(2.0f * xv, acc2[i][j], acc1[i][j]);
+        float d = dsc * fmaf(2.0f * xv, acc2[i][j], acc1[i][j]);
+        if ((a.flags & BBB_F_DX_PREACT) && !(xv > 0.0f)) d = 0.0f;   // gradient w.r.t. the pre-activation input
+        dxs[b * a.in + c + j] = d;
       }
     }
   }

@@ -403,42 +403,50 @@ def _lr_bwd(dy, mask, x, x_stride, p, eps, l, delta, sigma_p, S, B, flags, g_kl,
             'bbb_lr_linear_bwd')
 
 
-def _net_lr_forward(x2, params, sigma_p, S, eps, sample, calc_kl, kl):
+def _net_lr_forward(x2, params, sigma_p, S, eps, sample, calc_kl, kl, tf32=False):
     B = x2.shape[0]
-    ys, deltas = [], []
-    base = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if calc_kl else 0)
+    base = ((L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if calc_kl else 0) | (L.F_TF32 if tf32 else 0) |
+            L.F_OUT_ZEROED)
+    # one zero-filled buffer for every layer's y and delta: the tensor-core kernels add their split-K partial sums
+    # of x mu and x^2 sigma^2 into them before the epilogue turns them into the outputs
+    shapes = [(S, B, p[0].shape[1]) for p in params]
+    bufs = _zeroed_views(shapes + (shapes if sample else []), x2.device)
+    ys, deltas = bufs[:len(params)], (bufs[len(params):] if sample else [None] * len(params))
     inp, stride = x2, 0
     for l, p in enumerate(params):
         inn, out = p[0].shape
-        y = torch.empty((S, B, out), dtype=torch.float32, device=x2.device)
-        d = torch.empty_like(y) if sample else None
-        _lr_fwd(inp, stride, p, eps, l, sigma_p, S, B, base | (L.F_RELU_IN if l > 0 else 0), y, d, kl)
-        ys.append(y)
-        deltas.append(d)
-        inp, stride = y, B * out
+        _lr_fwd(inp, stride, p, eps, l, sigma_p, S, B, base | (L.F_RELU_IN if l > 0 else 0), ys[l], deltas[l], kl)
+        inp, stride = ys[l], B * out
     return ys, deltas
 
 
 def _net_lr_backward(x2, ys, deltas, d_out, params, sigma_p, S, eps, sample, calc_kl, g_kl, g_kl_dev, out_scale,
-                     need_dx0):
+                     need_dx0, tf32=False):
+    """Backward of _net_lr_forward.  As in the weight-sampling path every layer above the first hands down the
+    gradient w.r.t. the pre-activation output of the layer below (BBB_F_DX_PREACT).  In TF32 mode the kernels
+    overwrite the saved delta buffers with dV (they have no other use in the backward)."""
     B = x2.shape[0]
-    base = (L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if calc_kl else 0)
+    base = ((L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if calc_kl else 0) | (L.F_TF32 if tf32 else 0) |
+            L.F_OUT_ZEROED)
     grads = _alloc_grads(params)
     dy, dx0 = d_out, None
+    first = 0 if need_dx0 else 1
+    dxs = [None] * first + _zeroed_views([(S, B, p[0].shape[0]) for p in params[first:]], x2.device)
     for l in reversed(range(len(params))):
         p = params[l]
         inn, out = p[0].shape
         g = grads[l]
-        flags = base | (L.F_RELU_IN if l > 0 else 0)
+        flags = base | ((L.F_RELU_IN | L.F_DX_PREACT) if l > 0 else 0)
         want_dx = l > 0 or need_dx0
-        dx = torch.empty((S, B, inn), dtype=torch.float32, device=x2.device) if want_dx else None
+        dx = dxs[l] if want_dx else None
         if not want_dx:
             flags |= L.F_NO_DX
         if l == 0 and need_dx0:
             flags |= L.F_SCALE_DX
-        mask = ys[l] if l + 1 < len(params) else None
         x_in, stride = (x2, 0) if l == 0 else (ys[l - 1], B * inn)
-        _lr_bwd(dy, mask, x_in, stride, p, eps, l, deltas[l], sigma_p, S, B, flags, g_kl, g_kl_dev, out_scale, dx, g)
+        _lr_bwd(dy, None, x_in, stride, p, eps, l, deltas[l], sigma_p, S, B, flags, g_kl, g_kl_dev, out_scale, dx, g)
+        if grad_ready_hook is not None:
+            grad_ready_hook(l, g.flat)
         dy = dx
         if l == 0:
             dx0 = dx
@@ -502,15 +510,16 @@ class _MLPForwardLR(torch.autograd.Function):
     """S sampled forwards with LR layers -> outputs [S,B,C], kl [] (computed once, SURVEY B-8)."""
 
     @staticmethod
-    def forward(ctx, x2, sigma_p, S, sample, calc_kl, *flat):
+    def forward(ctx, x2, sigma_p, S, sample, calc_kl, tf32, *flat):
         L.require_cuda(x2, *flat)
         x2 = _f32c(x2)
         params = [tuple(_f32c(t) for t in flat[i:i + 4]) for i in range(0, len(flat), 4)]
         eps = plan_eps(_lr_eps_shapes(params, x2.shape[0]), S, x2.device, sample)
         kl = torch.zeros(1, dtype=torch.float64, device=x2.device)
-        ys, deltas = _net_lr_forward(x2, params, sigma_p, S, eps, sample, calc_kl, kl)
+        ys, deltas = _net_lr_forward(x2, params, sigma_p, S, eps, sample, calc_kl, kl, tf32)
         ctx.save_for_backward(x2, *flat, *ys, *[d for d in deltas if d is not None], *eps.tensors())
         ctx.cfg = (sigma_p, S, sample, calc_kl, eps, len(params), x2.requires_grad)
+        ctx.tf32 = tf32
         ctx.set_materialize_grads(False)
         return ys[-1], kl.to(torch.float32)[0]
 
@@ -527,21 +536,21 @@ class _MLPForwardLR(torch.autograd.Function):
         use_kl = calc_kl and dkl is not None
         g_kl_dev = _f32c(dkl).reshape(1) if use_kl else None
         dx0, grads = _net_lr_backward(x2, ys, deltas, _f32c(d_out), params, sigma_p, S, eps, sample, use_kl, 1.0,
-                                      g_kl_dev, None, x_rg)
+                                      g_kl_dev, None, x_rg, ctx.tf32)
         flat = [g for lg in grads for g in lg]
-        return (dx0.sum(0) if x_rg else None, None, None, None, None, *flat)
+        return (dx0.sum(0) if x_rg else None, None, None, None, None, None, *flat)
 
 
-def mlp_forward_lr(x2, layers, sigma_p, S, sample=True, calc_kl=True):
+def mlp_forward_lr(x2, layers, sigma_p, S, sample=True, calc_kl=True, tf32=False):
     flat = [t for layer in layers for t in layer]
-    return _MLPForwardLR.apply(x2, float(sigma_p), S, sample, calc_kl, *flat)
+    return _MLPForwardLR.apply(x2, float(sigma_p), S, sample, calc_kl, tf32, *flat)
 
 
 class _FusedELBOLR(torch.autograd.Function):
     """sample_elbo_lr (networks.py:211-225): loss = beta * KL + NLL / S, KL evaluated once."""
 
     @staticmethod
-    def forward(ctx, x2, target, beta, S, sigma, mode, sigma_p, *flat):
+    def forward(ctx, x2, target, beta, S, sigma, mode, sigma_p, tf32, *flat):
         L.require_cuda(x2, target, *flat)
         x2 = _f32c(x2)
         dev = x2.device
@@ -549,7 +558,7 @@ class _FusedELBOLR(torch.autograd.Function):
         eps = plan_eps(_lr_eps_shapes(params, x2.shape[0]), S, dev, True)
         acc = torch.zeros(2, dtype=torch.float64, device=dev)
         kl, nll = acc[0:1], acc[1:2]
-        ys, deltas = _net_lr_forward(x2, params, sigma_p, S, eps, True, True, kl)
+        ys, deltas = _net_lr_forward(x2, params, sigma_p, S, eps, True, True, kl, tf32)
         out = ys[-1]
         B, Cc = out.shape[1], out.shape[2]
         need_grad = any(t.requires_grad for t in flat)
@@ -568,6 +577,7 @@ class _FusedELBOLR(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *deltas, *eps.tensors())
         ctx.cfg = (sigma_p, S, beta_h, eps, len(params))
+        ctx.tf32 = tf32
         ctx.beta_dev = beta_d
         loss, klm, nl = out4[0:1], out4[1], out4[2:3]
         ctx.mark_non_differentiable(klm, nl)
@@ -584,14 +594,14 @@ class _FusedELBOLR(torch.autograd.Function):
         deltas = list(sv[o + nl - 1:o + 2 * nl - 1])
         scale = _f32c(g_loss).reshape(1)
         _, grads = _net_lr_backward(x2, ys, deltas, d_out, params, sigma_p, S, eps, True, True, beta, ctx.beta_dev,
-                                    scale, False)
+                                    scale, False, ctx.tf32)
         flat = [g for lg in grads for g in lg]
-        return (None,) * 7 + tuple(flat)
+        return (None,) * 8 + tuple(flat)
 
 
-def fused_elbo_lr(x2, target, beta, S, sigma, mode, sigma_p, layers):
+def fused_elbo_lr(x2, target, beta, S, sigma, mode, sigma_p, layers, tf32=False):
     flat = [t for layer in layers for t in layer]
-    return _FusedELBOLR.apply(x2, target, beta, S, sigma, mode, float(sigma_p), *flat)
+    return _FusedELBOLR.apply(x2, target, beta, S, sigma, mode, float(sigma_p), tf32, *flat)
 
 
 # =========================================================================================

@@ -74,6 +74,25 @@ class BayesianNetwork(nn.Module):
                 x = getattr(self, f'l{i + 1}_act')(x)
         return x
 
+    # ---- prediction: the reference's callers loop `net(x, sample=True)` test_samples times
+    # (class_task.py:81-87, reg_task.py:76-83); these run all the sampled forwards in one launch per layer ----
+    def sample_predict(self, x, samples):
+        """`samples` sampled forward passes at once -> outputs [samples, B, classes].  Same values, in the
+        reference eps mode the same draws in the same order, as `samples` calls of net(x, sample=True) in eval
+        mode (no log-probs are evaluated)."""
+        x2 = self._flat_input(x)
+        params = [l.params() for l in self.layers()]
+        with torch.no_grad():
+            if self.local_reparam:
+                outs, _ = F.mlp_forward_lr(x2, params, float(self.prior_init[0]), samples, True, False, self.tf32)
+            else:
+                outs, _, _ = F.mlp_forward(x2, params, self._prior, samples, True, False, self.tf32)
+        return outs
+
+    def predict_proba(self, x, samples):
+        """BNN_Classification.predict (class_task.py:81-87): softmax of every sampled forward, averaged."""
+        return torch.softmax(self.sample_predict(x, samples), dim=-1).mean(0)
+
     def log_prior(self):
         return sum(l.log_prior for l in self.layers())
 
@@ -131,8 +150,8 @@ class BayesianNetwork(nn.Module):
         params = [l.params() for l in self.layers()]
         sigma_p = float(self.prior_init[0])
         if self._fusable(x2, target):
-            return F.fused_elbo_lr(x2, target, beta, samples, sigma, self.mode, sigma_p, params)
-        outs, kl = F.mlp_forward_lr(x2, params, sigma_p, samples, True, True)
+            return F.fused_elbo_lr(x2, target, beta, samples, sigma, self.mode, sigma_p, params, self.tf32)
+        outs, kl = F.mlp_forward_lr(x2, params, sigma_p, samples, True, True, self.tf32)
         negative_log_likelihood = torch.zeros(1, device=outs.device)
         for i in range(samples):
             negative_log_likelihood = negative_log_likelihood + self.get_nll(outs[i], target, sigma)

@@ -249,7 +249,8 @@ class CallTimer:
             return r
 
         def call(*a):
-            if name == 'bbb_lr_linear_bwd':          # the LR backward is two kernels: time them one by one
+            if name == 'bbb_lr_linear_bwd' and not (a[17] & L.F_TF32):   # fp32 LR backward = two kernels, timed one by one
+                # (the TF32 LR backward overwrites delta with dV, so it cannot be run twice on the same buffers)
                 fi = 17
                 flags = a[fi]
                 r = 0
@@ -310,7 +311,7 @@ def run_b200(args):
     w = dict(WORKLOADS[args.workload])
     S = args.samples or w['S']                 # per-GPU MC samples (weak scaling over the sample axis)
     # default: the tcgen05 kind::tf32 path where the layers are wide enough to be dense contractions
-    tf32 = (args.tf32 == 1) or (args.tf32 < 0 and args.workload in ('mnist', 'wide'))
+    tf32 = (args.tf32 == 1) or (args.tf32 < 0 and args.workload in ('mnist', 'mnist_lr', 'wide'))
     mp = model_params(w)
     mp['tf32'] = tf32
     torch.manual_seed(0)

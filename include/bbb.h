@@ -144,7 +144,10 @@ int bbb_lr_linear_fwd(const float *x, int64_t x_sample_stride, const float *w_mu
                       int32_t flags, float *y, float *delta, double *kl, void *stream);
 
 /* backward of the above.  g_kl = d loss / d kl (host scalar), times
- * g_kl_dev[0] when non-NULL; out_scale_dev as in bbb_linear_bwd. */
+ * g_kl_dev[0] when non-NULL; out_scale_dev as in bbb_linear_bwd.
+ * With BBB_F_TF32 (tcgen05 path: B <= 128, in and out multiples of 4, no dy_mask_src) the call OVERWRITES `delta`
+ * with dV = dz eps_a / (2 delta), which the two contractions of the backward consume; delta has no other use in
+ * the backward, but a caller must not run the backward twice on the same forward buffers in that mode. */
 int bbb_lr_linear_bwd(const float *dy, const float *dy_mask_src, const float *x, int64_t x_sample_stride,
                       const float *w_mu, const float *w_rho, const float *b_mu, const float *b_rho,
                       const float *eps_a, const float *eps_b, const bbb_rng *rng, const float *delta,

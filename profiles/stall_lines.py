@@ -12,7 +12,7 @@ for r in rows:
         cur = r[1].split('/')[-1]
         continue
     if len(r) > 8 and r[0].isdigit() and r[7].isdigit():
-        n, s = int(r[7]), int(r[6] or 0)
+        n, s = int(r[7]), (int(r[6]) if r[6].isdigit() else 0)
         tot += s
         out.append((s, n, cur, int(r[0]), r[1].strip()[:105]))
 out.sort(reverse=True)

@@ -208,7 +208,11 @@ class FakeLib:
                 acc_b += dz.sum(0) * EB[s]
             if DX is not None:
                 v = dz @ WM.T + 2 * xs_ * (dV @ (sw * sw).T)
-                DX[s] = (v * (osc if flags & F_SCALE_DX else 1.0)).astype(np.float32)
+                v = v * (osc if flags & F_SCALE_DX else 1.0)
+                if flags & F_DX_PREACT:
+                    assert relu
+                    v = v * (x_pre > 0)
+                DX[s] = v.astype(np.float32)
         a_wr = CF.sigmoid(WR) * (2 * sw * acc_v + gk * (sw / sp2 - 1 / sw))
         a_br = CF.sigmoid(BR) * (acc_b + gk * (sb / sp2 - 1 / sb))
         for ptr, shape, val in ((gwm, (inn, out), a_wm), (gwr, (inn, out), a_wr), (gbm, (out,), a_bm),

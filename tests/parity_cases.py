@@ -122,3 +122,24 @@ def check_state_dict(case, device):
     want = (d[0], d[1]) if case.lr else (d[1], d[0])
     assert tuple(net.l1.weight_mu.shape) == want
     assert all(('mu' in n) or ('rho' in n) for n, _ in net.named_parameters())
+
+
+def check_batched_prediction(case, device, samples=4, rtol=1e-5):
+    """net.sample_predict (one launch per layer for all sampled forwards) == the reference's loop of
+    net(x, sample=True) calls in eval mode, same seed."""
+    net = build_net(case, device)
+    net.eval()
+    x = case.x.to(device)
+    with torch.no_grad(), bnn_b200.eps_mode('reference'):
+        torch.manual_seed(123)
+        want = torch.stack([net(x, sample=True) for _ in range(samples)])
+        torch.manual_seed(123)
+        got = net.sample_predict(x, samples)
+    assert tuple(got.shape) == tuple(want.shape)
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=rtol, atol=1e-6)
+    if case.mode == 'classification':
+        with torch.no_grad(), bnn_b200.eps_mode('reference'):
+            torch.manual_seed(123)
+            p = net.predict_proba(x, samples)
+        np.testing.assert_allclose(p.sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
+        np.testing.assert_allclose(p.cpu().numpy(), torch.softmax(want, -1).mean(0).cpu().numpy(), rtol=1e-4, atol=1e-6)

@@ -36,6 +36,11 @@ def test_eval_modes(name):
     PC.check_eval_modes(Case(name), DEV)
 
 
+@pytest.mark.parametrize('name', SMALL + SMALL_LR + ['cfg4_bandit'])
+def test_batched_prediction(name):
+    PC.check_batched_prediction(Case(name), DEV)
+
+
 def test_native_library_is_loaded():
     import ctypes
     assert isinstance(bnn_b200._lib.lib(), ctypes.CDLL)

@@ -10,7 +10,7 @@ import torch
 
 import bnn_b200
 from tests import parity_cases as PC
-from tests.golden_util import Case, SMALL, BIG
+from tests.golden_util import Case, SMALL, BIG, SMALL_LR, BIG_LR
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -32,10 +32,13 @@ def test_tcgen05_plain_gemm(B, d_in, d_out):
     assert err < 2e-3, float(err)
 
 
-@pytest.mark.parametrize('name', SMALL + BIG)
+@pytest.mark.parametrize('name', SMALL + BIG + SMALL_LR + BIG_LR)
 @pytest.mark.parametrize('fused', [True, False])
 def test_tf32_train_step_matches_reference(name, fused):
-    PC.check_train_step(Case(name), DEV, fused=fused, rtol=1e-5, rtol_gemm=RTOL_TF32, tf32=True)
+    c = Case(name)
+    # LR: the backward divides by delta = sqrt(x^2 sigma^2), which amplifies the TF32 rounding of the variance
+    # contraction (measured 1.0e-2 on l1.weight_mu at the MNIST-shape config): stated bound 2e-2 for that estimator
+    PC.check_train_step(c, DEV, fused=fused, rtol=1e-5, rtol_gemm=2e-2 if c.lr else RTOL_TF32, tf32=True)
 
 
 @pytest.mark.parametrize('S', [1, 2, 3, 5])

@@ -157,3 +157,8 @@ def test_fuse_optimizer_refuses_what_the_kernel_cannot_do(fake):
     assert net.fuse_optimizer(bnn_b200.FusedAdam(net.parameters())) is False and net._fused_opt is None
     net = PC.build_net(Case('small_lr_cls'), 'cpu')
     assert net.fuse_optimizer(bnn_b200.FusedAdam(net.parameters())) is False
+
+
+@pytest.mark.parametrize('name', SMALL + SMALL_LR)
+def test_batched_prediction(fake, name):
+    PC.check_batched_prediction(Case(name), 'cpu')
