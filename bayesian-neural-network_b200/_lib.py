@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libbbb.so')
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
 F_OUT_ZEROED, F_DX_PREACT = 256, 512
 PRIOR_GAUSSIAN, PRIOR_MIXTURE = 0, 1
+NLL_NONE, NLL_CE, NLL_GAUSS = 0, 1, 2
 
 
 class Rng(C.Structure):
@@ -48,6 +49,8 @@ _SIGS = {
     'bbb_philox_fill_normal': ([P, I64, U64, U32, U32, U32, P], C.c_int),
     'bbb_nll_ce': ([P, P, I64, I64, I64, F32, P, P, P], C.c_int),
     'bbb_nll_gauss': ([P, P, F32, I64, I64, I64, F32, P, P, P], C.c_int),
+    'bbb_head_fwd': ([P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, I32, P, F32, F32, P, P, P, P, P, F32,
+                      P, P, P, P], C.c_int),
     'bbb_elbo_finalize': ([P, P, P, P, I64, F32, P, P, P], C.c_int),
     'bbb_adam_step': ([I32, P, P, P, P, P, F64, F64, F64, F64, U32, P, P, P], C.c_int),
     'bbb_counter_add': ([P, U32, P], C.c_int),

@@ -38,6 +38,7 @@ extern "C" int bbb_linear_fwd(const float *x, int64_t x_sample_stride, const flo
   a.vec_in = (in % 4 == 0) && all16({x, w_mu, w_rho, eps_w});
   a.vec_out = (out % 4 == 0) && all16({y});
   cudaStream_t st = (cudaStream_t)stream;
+  if (head_supported(a)) return launch_linear_fwd_head(a, st);                // out <= 16, both modes, exact fp32
   if ((flags & BBB_F_TF32) && linear_sk_supported(a)) return launch_linear_fwd_sk(a, st);
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_fwd_tc(a, st);
   if (linear_narrow_supported(a)) return launch_linear_fwd_narrow(a, st);   // exact-fp32 mode, out <= 16
@@ -92,6 +93,7 @@ int linear_bwd_impl(const float *dy, const float *dy_mask_src, const float *x, i
     a.adam_lr = adam->lr; a.adam_b1 = adam->beta1; a.adam_b2 = adam->beta2; a.adam_eps = (float)adam->eps;
     a.adam_step = adam->step; a.adam_step_dev = adam->step_dev; a.adam_lr_scale_dev = adam->lr_scale_dev;
   }
+  if (!adam && a.S > 0 && head_supported(a)) return launch_linear_bwd_head(a, st);   // out <= 16, both modes, exact fp32
   if ((flags & BBB_F_TF32) && a.S > 0 && linear_bwd_fused_supported(a)) return launch_linear_bwd_fused(a, st);
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_bwd_tc(a, st);
   if (a.S > 0 && linear_narrow_supported(a)) return launch_linear_bwd_narrow(a, st);   // exact-fp32 mode, out <= 16

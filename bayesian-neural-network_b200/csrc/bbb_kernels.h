@@ -84,6 +84,12 @@ bool lr_narrow_supported(const LrArgs &a);
 int launch_lr_fwd_narrow(const LrArgs &a, cudaStream_t st);
 int launch_lr_bwd_narrow(const LrArgs &a, cudaStream_t st);
 
+// the network's head (out <= 16), exact fp32, cluster split-K forward (+ likelihood + ELBO assembly through
+// bbb_head_fwd) and column-owned backward (bbb_head.cu)
+bool head_supported(const LinArgs &a);
+int launch_linear_fwd_head(const LinArgs &a, cudaStream_t st);
+int launch_linear_bwd_head(const LinArgs &a, cudaStream_t st);
+
 // fused backward (wgrad + analytic epilogue + dgrad, one eps regeneration) for batches of at most 128 rows
 // (bbb_linear_bwd_fused.cu)
 bool linear_bwd_fused_supported(const LinArgs &a);

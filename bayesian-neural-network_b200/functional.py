@@ -159,9 +159,30 @@ def _zeroed_views(shapes, device):
     return out
 
 
-def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq, ys=None):
+def head_eligible(p):
+    """bbb_head_fwd's shape conditions (include/bbb.h): a narrow last layer whose rows are 16-byte multiples."""
+    out, inn = p[0].shape
+    return out <= 16 and inn % 4 == 0 and 4 <= inn <= 8192
+
+
+def _ws_head(x, x_stride, p, eps, l, prior, S, B, flags, y, logp, logq, mode, target, sigma, d_out, nll, beta_h,
+             beta_d, out4, done):
+    """Last layer + likelihood (+ its gradient) + ELBO assembly in one launch (bbb_head_fwd)."""
+    wm, wr, bm, br = p
+    out, inn = wm.shape
+    ew, eb = eps.ptrs(l)
+    rng = eps.rng(l)
+    kind = L.NLL_CE if mode == 'classification' else L.NLL_GAUSS
+    L.check(L.lib().bbb_head_fwd(L.ptr(x), x_stride, L.ptr(wm), L.ptr(wr), L.ptr(bm), L.ptr(br), ew, eb,
+                                 C.byref(rng), C.byref(prior), S, B, inn, out, flags, kind, L.ptr(target),
+                                 float(sigma), 1.0 / S, L.ptr(y), L.ptr(d_out), L.ptr(logp), L.ptr(logq), L.ptr(nll),
+                                 beta_h, L.ptr(beta_d), L.ptr(out4), L.ptr(done), L.stream()), 'bbb_head_fwd')
+
+
+def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq, ys=None, head=None):
     """All layers, all S samples.  Returns the list of pre-activation outputs ys[l] = [S,B,out_l]
-    (written into the zero-filled `ys` when the caller supplies them)."""
+    (written into the zero-filled `ys` when the caller supplies them).  `head(inp, stride, flags, y)`, when given,
+    runs the last layer instead of bbb_linear_fwd (the fused ELBO tail)."""
     B = x2.shape[0]
     base = ((L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if logprob else 0) | (L.F_TF32 if tf32 else 0) |
             L.F_OUT_ZEROED)
@@ -170,7 +191,11 @@ def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq
     inp, stride = x2, 0
     for l, p in enumerate(params):
         out, inn = p[0].shape
-        _ws_fwd(inp, stride, p, eps, l, prior, S, B, base | (L.F_RELU_IN if l > 0 else 0), ys[l], logp, logq)
+        flags = base | (L.F_RELU_IN if l > 0 else 0)
+        if head is not None and l == len(params) - 1:
+            head(inp, stride, flags, ys[l])
+        else:
+            _ws_fwd(inp, stride, p, eps, l, prior, S, B, flags, ys[l], logp, logq)
         inp, stride = ys[l], B * out
     return ys
 
@@ -317,30 +342,41 @@ class _FusedELBO(torch.autograd.Function):
         eps = plan_eps([(tuple(p[0].shape), (p[0].shape[0],)) for p in params], S, dev, True)
         need_grad = any(t.requires_grad for t in flat)
         B = x2.shape[0]
-        # ONE zero-filled workspace (one memset per step): fp64 accumulators | activations of every layer | dx of
-        # every layer above the first (the backward's split-K kernels add into them)
-        shapes = [(2 * (2 * S + 1),)] + [(S, B, p[0].shape[0]) for p in params]
+        # ONE zero-filled workspace (one memset per step): fp64 accumulators + the head's completion counter |
+        # activations of every layer | dx of every layer above the first (the backward's split-K kernels add into them)
+        shapes = [(2 * (2 * S + 1) + 2,)] + [(S, B, p[0].shape[0]) for p in params]
         if need_grad:
             shapes += [(S, B, p[0].shape[1]) for p in params[1:]]
         ws = _zeroed_views(shapes, dev)
-        acc = ws[0].view(torch.float64)
+        acc = ws[0][:2 * (2 * S + 1)].view(torch.float64)
+        done = ws[0][2 * (2 * S + 1):]
         ys, dxs = ws[1:1 + len(params)], ([None] + ws[1 + len(params):] if need_grad else None)
         logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
-        ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq, ys)
-        out = ys[-1]
-        Cc = out.shape[2]
-        d_out = torch.empty_like(out) if need_grad else None
-        if mode == 'classification':
-            L.check(L.lib().bbb_nll_ce(L.ptr(out), L.ptr(target), S, B, Cc, 1.0 / S, L.ptr(nll), L.ptr(d_out),
-                                       L.stream()), 'bbb_nll_ce')
-        else:
-            tgt = _f32c(target)
-            L.check(L.lib().bbb_nll_gauss(L.ptr(out), L.ptr(tgt), float(sigma), S, B, Cc, 1.0 / S, L.ptr(nll),
-                                          L.ptr(d_out), L.stream()), 'bbb_nll_gauss')
+        Cc = params[-1][0].shape[0]
+        d_out = torch.empty((S, B, Cc), dtype=torch.float32, device=dev) if need_grad else None
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
         beta_h, beta_d = _split_beta(beta)
-        L.check(L.lib().bbb_elbo_finalize(L.ptr(logp), L.ptr(logq), None, L.ptr(nll), S, beta_h, L.ptr(beta_d),
-                                          L.ptr(out4), L.stream()), 'bbb_elbo_finalize')
+        if head_eligible(params[-1]):
+            # the last layer, the likelihood with its gradient and the assembly of the four scalars: one launch
+            tgt = target if mode == 'classification' else _f32c(target)
+            nl = len(params) - 1
+
+            def head(inp, stride, flags, y):
+                _ws_head(inp, stride, params[nl], eps, nl, prior, S, B, flags, y, logp, logq, mode, tgt, sigma, d_out,
+                         nll, beta_h, beta_d, out4, done)
+            ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq, ys, head)
+        else:
+            ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq, ys)
+            out = ys[-1]
+            if mode == 'classification':
+                L.check(L.lib().bbb_nll_ce(L.ptr(out), L.ptr(target), S, B, Cc, 1.0 / S, L.ptr(nll), L.ptr(d_out),
+                                           L.stream()), 'bbb_nll_ce')
+            else:
+                tgt = _f32c(target)
+                L.check(L.lib().bbb_nll_gauss(L.ptr(out), L.ptr(tgt), float(sigma), S, B, Cc, 1.0 / S, L.ptr(nll),
+                                              L.ptr(d_out), L.stream()), 'bbb_nll_gauss')
+            L.check(L.lib().bbb_elbo_finalize(L.ptr(logp), L.ptr(logq), None, L.ptr(nll), S, beta_h, L.ptr(beta_d),
+                                              L.ptr(out4), L.stream()), 'bbb_elbo_finalize')
         if need_grad:
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *eps.tensors())
             ctx.dxs = dxs

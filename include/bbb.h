@@ -179,6 +179,27 @@ int bbb_nll_ce(const float *logits, const int64_t *target, int64_t S, int64_t B,
 int bbb_nll_gauss(const float *out, const float *target, float sigma, int64_t S, int64_t B, int64_t D,
                   float grad_scale, double *nll, float *dout, void *stream);
 
+/* ---- the network's head in one launch --------------------------------------------------------
+ * bbb_head_fwd = bbb_linear_fwd of a narrow layer (out <= 16: the classification / regression head, networks.py:164)
+ * + bbb_nll_ce / bbb_nll_gauss on its outputs + bbb_elbo_finalize, i.e. the tail of sample_elbo (networks.py:199-209)
+ * from the last layer's forward to the four returned scalars.  Exact fp32, deterministic.
+ *   nll_kind  BBB_NLL_NONE: plain layer forward (target, nll, dy, out4 ignored);  BBB_NLL_CE: target = int64 [B];
+ *             BBB_NLL_GAUSS: target = float [B,out], sigma = likelihood std
+ *   y  [S,B,out] written;  dy (nullable) [S,B,out] = grad_scale * d nll / d y;  nll += sum over (s, b)
+ *   logp, logq [S] += this layer's terms (BBB_F_LOGPROB); they must already hold the other layers' sums when out4 is
+ *             requested, because the CTA that finishes last assembles out4 exactly as bbb_elbo_finalize does
+ *   done_counter  zeroed device word used to find that CTA (required with out4; left zero again)
+ * Needs in % 4 == 0, in <= 8192 and 16-byte aligned x / w rows; returns BBB_EUNSUPPORTED otherwise. */
+#define BBB_NLL_NONE 0
+#define BBB_NLL_CE 1
+#define BBB_NLL_GAUSS 2
+int bbb_head_fwd(const float *x, int64_t x_sample_stride, const float *w_mu, const float *w_rho,
+                 const float *b_mu, const float *b_rho, const float *eps_w, const float *eps_b,
+                 const bbb_rng *rng, const bbb_prior *prior, int64_t S, int64_t B, int64_t in, int64_t out,
+                 int32_t flags, int32_t nll_kind, const void *target, float sigma, float grad_scale,
+                 float *y, float *dy, double *logp, double *logq, double *nll, float beta,
+                 const float *beta_dev, float *out4, uint32_t *done_counter, void *stream);
+
 /* ELBO assembly (networks.py:205-209 / 221-225):
  * out4 = { beta mean(logq) - beta mean(logp) + nll/S, mean(logp), mean(logq), nll/S }   (kl == NULL)
  * out4 = { beta kl + nll/S, kl, nll/S, 0 }                                              (kl != NULL)

@@ -268,6 +268,23 @@ class FakeLib:
                 G[s] = (scale * g).astype(np.float32)
         return 0
 
+    def bbb_head_fwd(self, x, xs, wm, wr, bm, br, ew, eb, rng, prior, S, B, inn, out, flags, nll_kind, target, sigma,
+                     scale, y, dy, logp, logq, nll, beta, beta_dev, out4, done, st):
+        """last layer + likelihood + ELBO assembly: the composition of the three calls it replaces"""
+        assert out <= 16 and inn % 4 == 0, 'fake lib: bbb_head_fwd shape conditions'
+        self.bbb_linear_fwd(x, xs, wm, wr, bm, br, ew, eb, rng, prior, S, B, inn, out, flags, y, logp, logq, st)
+        self.calls[-1] = 'head_fwd'
+        if nll_kind == 1:
+            self.bbb_nll_ce(y, target, S, B, out, scale, nll, dy, st)
+            self.calls.pop()
+        elif nll_kind == 2:
+            self.bbb_nll_gauss(y, target, sigma, S, B, out, scale, nll, dy, st)
+            self.calls.pop()
+        if out4:
+            assert done and _arr(done, C.c_uint32, 1)[0] == 0, 'fake lib: done counter must be zeroed'
+            self.bbb_elbo_finalize(logp, logq, None, nll, S, beta, beta_dev, out4, st)
+        return 0
+
     def bbb_elbo_finalize(self, logp, logq, kl, nll, S, beta, beta_dev, out4, st):
         O = _f(out4, 4)
         if beta_dev:

@@ -24,7 +24,7 @@ def fake(monkeypatch):
 @pytest.mark.parametrize('fused', [True, False])
 def test_train_step_network_level(fake, name, fused):
     PC.check_train_step(Case(name), 'cpu', fused=fused)
-    fused_used = ('nll_ce' in fake.calls) or ('nll_gauss' in fake.calls)
+    fused_used = ('nll_ce' in fake.calls) or ('nll_gauss' in fake.calls) or ('head_fwd' in fake.calls)
     case = Case(name)
     expect_fused = fused and not case.meta.get('flat_target', False)
     assert fused_used == expect_fused        # [B] vs [B,1] broadcast targets (SURVEY B-3) take the general path
