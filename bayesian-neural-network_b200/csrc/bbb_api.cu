@@ -40,6 +40,7 @@ extern "C" int bbb_linear_fwd(const float *x, int64_t x_sample_stride, const flo
   cudaStream_t st = (cudaStream_t)stream;
   if (head_supported(a)) return launch_linear_fwd_head(a, st);                // out <= 16, both modes, exact fp32
   if ((flags & BBB_F_TF32) && linear_sk_supported(a)) return launch_linear_fwd_sk(a, st);
+  if ((flags & BBB_F_TF32) && linear_big_fwd_supported(a)) return launch_linear_fwd_big(a, st);   // batch >= 384
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_fwd_tc(a, st);
   if (linear_narrow_supported(a)) return launch_linear_fwd_narrow(a, st);   // exact-fp32 mode, out <= 16
   return launch_linear_fwd_fma(a, st);
@@ -95,7 +96,21 @@ int linear_bwd_impl(const float *dy, const float *dy_mask_src, const float *x, i
   }
   if (!adam && a.S > 0 && head_supported(a)) return launch_linear_bwd_head(a, st);   // out <= 16, both modes, exact fp32
   if ((flags & BBB_F_TF32) && a.S > 0 && linear_bwd_fused_supported(a)) return launch_linear_bwd_fused(a, st);
-  if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_bwd_tc(a, st);
+  if ((flags & BBB_F_TF32) && linear_tc_supported(a)) {
+    // batch >= 384: batch-resident dgrad and the MN-major wgrad (bbb_linear_big.cu); anything they do not cover
+    // goes to the batch-tiled kernels
+    LinArgs rest = a;
+    if (a.S > 0 && !(flags & BBB_F_NO_DX) && linear_big_dgrad_supported(a)) {
+      if (int r = launch_linear_dgrad_big(a, st)) return r;
+      rest.flags |= BBB_F_NO_DX;
+    }
+    if (a.S > 0 && !(flags & BBB_F_NO_WGRAD) && linear_big_wgrad_supported(a)) {
+      if (int r = launch_linear_wgrad_big(a, st)) return r;
+      rest.flags |= BBB_F_NO_WGRAD;
+    }
+    if ((rest.flags & BBB_F_NO_DX) && (rest.flags & BBB_F_NO_WGRAD)) return BBB_OK;
+    return launch_linear_bwd_tc(rest, st);
+  }
   if (a.S > 0 && linear_narrow_supported(a)) return launch_linear_bwd_narrow(a, st);   // exact-fp32 mode, out <= 16
   return launch_linear_bwd_fma(a, st);
 }

@@ -35,12 +35,16 @@ constexpr int NO = 16;     // widest output handled
 struct HQuad {
   float mu[4], sg[4], ep[4], w[4];
 };
+// Parameters and the RNG step counter are read with ld.global.cg (L2 only): every element is read once.
+__device__ __forceinline__ void head_rng_resolve(RngDev &rng) {
+  if (rng.step_dev) rng.step += __ldcg(rng.step_dev);
+}
 // mu, sigma, eps, w of the 4 weights at linear element e (e % 4 == 0) of sample s
 __device__ __forceinline__ void head_quad(const LinArgs &a, int s, int64_t e, bool sample, bool need_sigma, HQuad &q) {
-  const float4 m = __ldg(reinterpret_cast<const float4 *>(a.w_mu + e));
+  const float4 m = __ldcg(reinterpret_cast<const float4 *>(a.w_mu + e));
   q.mu[0] = m.x; q.mu[1] = m.y; q.mu[2] = m.z; q.mu[3] = m.w;
   if (sample || need_sigma) {
-    const float4 r = __ldg(reinterpret_cast<const float4 *>(a.w_rho + e));
+    const float4 r = __ldcg(reinterpret_cast<const float4 *>(a.w_rho + e));
     q.sg[0] = softplus_f(r.x); q.sg[1] = softplus_f(r.y); q.sg[2] = softplus_f(r.z); q.sg[3] = softplus_f(r.w);
   }
   if (sample) {
@@ -59,8 +63,8 @@ __device__ __forceinline__ void head_quad(const LinArgs &a, int s, int64_t e, bo
 }
 __device__ __forceinline__ void head_bias(const LinArgs &a, int s, int64_t o, bool sample, bool need_sigma, float &b,
                                           float &sg, float &ep) {
-  const float mu = __ldg(a.b_mu + o);
-  sg = (sample || need_sigma) ? softplus_f(__ldg(a.b_rho + o)) : 0.0f;
+  const float mu = __ldcg(a.b_mu + o);
+  sg = (sample || need_sigma) ? softplus_f(__ldcg(a.b_rho + o)) : 0.0f;
   ep = 0.0f;
   if (sample)
     ep = a.eps_b ? __ldg(a.eps_b + (int64_t)s * a.out + o)
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(FT, 1) head_fwd_kernel(const LinArgs a_in, con
   pdl_launch_dependents();
   pdl_wait();
   LinArgs a = a_in;
-  rng_resolve(a.rng);
+  head_rng_resolve(a.rng);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_rank(), cln = cluster_size();
   const int cl = blockIdx.x / (int)cln;
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const LinArgs a_in, int cw
   pdl_launch_dependents();
   pdl_wait();
   LinArgs a = a_in;
-  rng_resolve(a.rng);
+  head_rng_resolve(a.rng);
   float *dz_s = dynb, *x_s = dynb + RP * DZP;
   const int tid = threadIdx.x;
   const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN, wgrad = !(a.flags & BBB_F_NO_WGRAD);
@@ -379,8 +383,6 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const LinArgs a_in, int cw
   const int w = (int)min((int64_t)cw, a.in - i_lo), nqc = w >> 2;   // columns / quads of this CTA
   const int per = out * nqc;                                         // weight quads of this CTA
   const bool bias_cta = blockIdx.x == 0;
-  const float osc = a.out_scale_dev ? __ldg(a.out_scale_dev) : 1.0f;
-  const float dxs = ((a.flags & BBB_F_SCALE_DX) && a.out_scale_dev) ? osc : 1.0f;
 
   // item slot -> (sample of the pass, o, column quad); batch group of this thread for the wgrad partial sums
   const int slot = tid & (SLOTS - 1), grp = tid / SLOTS;
@@ -390,12 +392,18 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const LinArgs a_in, int cw
   // owner thread t < per accumulates the gradient of weight quad t over all samples
   float gm[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
   float gbm = 0.0f, gbr = 0.0f;
+  HQuad hq;
+  auto sample_item = [&](int s0) {
+    head_quad(a, s0 + it_sl, it_e, sample, true, hq);
+    *reinterpret_cast<float4 *>(&Wt[(it_sl * NO + it_o) * CWM + it_q * 4]) = make_float4(hq.w[0], hq.w[1], hq.w[2], hq.w[3]);
+  };
+  const float osc = a.out_scale_dev ? __ldg(a.out_scale_dev) : 1.0f;
+  const float dxs = ((a.flags & BBB_F_SCALE_DX) && a.out_scale_dev) ? osc : 1.0f;
 
   for (int s0 = 0; s0 < a.S; s0 += spp) {
     const int ns = min(spp, a.S - s0);
     const int items = ns * per;
     const bool item_ok = slot < items;
-    HQuad hq;
     float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
     float cacc = 0.0f;
     bool need_sample = true;
@@ -424,11 +432,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const LinArgs a_in, int cw
       // 2. the item threads sample their weight quad while those loads are in flight
       if (need_sample) {
         need_sample = false;
-        if (ithread && item_ok) {
-          head_quad(a, s0 + it_sl, it_e, sample, true, hq);
-          *reinterpret_cast<float4 *>(&Wt[(it_sl * NO + it_o) * CWM + it_q * 4]) =
-              make_float4(hq.w[0], hq.w[1], hq.w[2], hq.w[3]);
-        }
+        if (ithread && item_ok) sample_item(s0);
       }
       if (p_ok) {          // the previous pass was consumed before its barrier (C)
 #pragma unroll

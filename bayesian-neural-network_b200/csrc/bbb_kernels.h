@@ -72,6 +72,15 @@ bool linear_tc_supported(const LinArgs &a);
 int launch_linear_fwd_tc(const LinArgs &a, cudaStream_t st);
 int launch_linear_bwd_tc(const LinArgs &a, cudaStream_t st);
 
+// tcgen05 kind::tf32 forward / dgrad for large batches (bbb_linear_big.cu): the batch is the MMA's N dimension, a CTA's
+// accumulator [128 weight rows x 512 batch rows] fills TMEM, every sampled weight tile is used for 512 batch rows
+bool linear_big_fwd_supported(const LinArgs &a);
+bool linear_big_dgrad_supported(const LinArgs &a);
+int launch_linear_fwd_big(const LinArgs &a, cudaStream_t st);
+int launch_linear_dgrad_big(const LinArgs &a, cudaStream_t st);
+bool linear_big_wgrad_supported(const LinArgs &a);
+int launch_linear_wgrad_big(const LinArgs &a, cudaStream_t st);   // plain MN-major GEMM over the batch + sampling epilogue
+
 // tcgen05 kind::tf32 forward for batches of at most 128 rows (bbb_linear_sk.cu): stream-K, two co-resident CTAs per SM.
 bool linear_sk_supported(const LinArgs &a);
 int launch_linear_fwd_sk(const LinArgs &a, cudaStream_t st);

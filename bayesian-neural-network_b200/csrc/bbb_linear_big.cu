@@ -1,0 +1,526 @@
+// Weight-sampling Bayesian linear layer on tcgen05 kind::tf32 for LARGE batches (BASELINE.json config 5: 4096-wide
+// layers, batch 4096): forward and dgrad.
+//
+// At these sizes the contraction is dense (137 GFLOP per layer and sample) but every weight that enters it costs
+// ~100 CUDA-core instructions to sample (Philox + Box-Muller + softplus [+ log-densities]).  What decides the speed is
+// therefore how many batch rows a sampled weight tile is used for before it is thrown away.  bbb_linear_tc.cu gives a
+// CTA one 128-row batch tile, so W is re-sampled B / 128 = 32 times; here the operands are swapped so that the BATCH
+// is the MMA's N dimension and a CTA's accumulator fills all of TMEM:
+//
+//   D^T[m][b] (+)= A[m][k] * Bop[b][k]     M = 128 weight rows, N = 512 batch rows (two N = 256 MMAs), K = 32 / stage
+//     forward:  A = W_s[o][k]   sampled in registers, K-major SWIZZLE_128B      Bop = x_s[b][k]  (ReLU on load)
+//     dgrad:    A = W_s^T[i][o] sampled along i (coalesced), scattered K-major   Bop = dz_s[b][o]
+//
+// so a weight tile is sampled B / 512 = 8 times (4x less sampling work for the same MMAs), and the drain needs no
+// shared-memory transpose: TMEM hands a warp 32 consecutive weight rows of one batch column, which is a coalesced
+// 128-byte store into the row-major y[b][o] / dx[b][i].
+//   Warp-specialised: 16 producer warps stage the activation tile and sample the weight tile into a 2-stage ring
+//   (full / empty mbarriers), one warp issues the MMAs; 1 CTA per SM (160 KB of operands, 512 TMEM columns).
+//   Grid (weight-row tiles, batch tiles of 512, samples); batch tile 0 also accumulates the log-prob terms.
+// W never leaves the SM; eps is regenerated from the same Philox coordinates in the backward.
+#include "bbb_tc_tiles.cuh"
+
+namespace bbb {
+namespace {
+
+using namespace tc;
+using namespace tcx;
+
+constexpr int PW = 16;                    // producer warps
+constexpr int PT = PW * 32;               // producer threads
+constexpr int BT = PT + 32;               // + the MMA-issuing warp
+constexpr int NBT = 512;                  // batch rows per CTA tile = TMEM columns
+constexpr int NSTG = 2;
+constexpr int A_BYTES = BM * 128;         // [128 weight rows][32 k]
+constexpr int B_BYTES = NBT * 128;        // [512 batch rows][32 k]
+constexpr int STAGE = A_BYTES + B_BYTES;  // 80 KB
+constexpr int kBigDyn = NSTG * STAGE + 1024;
+
+struct BCtl {
+  uint64_t full[NSTG], empty[NSTG], acc;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mbar_arrive1(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// kDgrad = false: forward (A = W tile, rows = output features o, K = input features)
+// kDgrad = true : dgrad   (A = W^T tile, rows = input features i, K = output features)
+template <bool kDgrad, bool kLogProb>
+__global__ void __launch_bounds__(BT, 1) big_kernel(const LinArgs a_in) {
+  extern __shared__ uint8_t dsm[];
+  __shared__ BCtl ctl;
+  __shared__ float red[64];
+  LinArgs a = a_in;
+  uint8_t *tiles = align1024(dsm);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool sample = a.flags & BBB_F_SAMPLE, relu = !kDgrad && (a.flags & BBB_F_RELU_IN);
+  const int s = blockIdx.z;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * NBT;
+  const int64_t Mdim = kDgrad ? a.in : a.out, Kdim = kDgrad ? a.out : a.in;
+  const int nkb = (int)((Kdim + BK - 1) / BK);
+  const bool lpcta = kLogProb && blockIdx.y == 0;   // one batch tile per (weight tile, sample) owns the log-prob terms
+
+  // ---- setup: TMEM (all 512 columns), barriers ------------------------------------------------
+  if (warp == PW) tmem_alloc(smem_u32(&ctl.tmem_base), 512);
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < NSTG; ++st) {
+      mbar_init(smem_u32(&ctl.full[st]), PW);
+      mbar_init(smem_u32(&ctl.empty[st]), 1);
+    }
+    mbar_init(smem_u32(&ctl.acc), 1);
+    mbar_fence_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = ctl.tmem_base;
+  pdl_wait();
+  rng_resolve(a.rng);
+  float lp = 0.0f, lq = 0.0f;
+
+  if (warp == PW) {
+    // ---- MMA warp ---------------------------------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(BM, 256);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % NSTG;
+        mbar_wait_parked(smem_u32(&ctl.full[st]), (uint32_t)((kb / NSTG) & 1));
+        tc_fence_after_sync();
+        const uint32_t As = smem_u32(tiles + st * STAGE), Bs = As + A_BYTES;
+        const uint64_t da = smem_desc_sw128(As);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t db = smem_desc_sw128(Bs + h * 256 * 128);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_tf32(tmem + h * 256, da + 2u * kk, db + 2u * kk, idesc, (kb == 0 && kk == 0) ? 0u : 1u);
+        }
+        mma_commit(smem_u32(&ctl.empty[st]));
+      }
+      mma_commit(smem_u32(&ctl.acc));
+    }
+    __syncwarp();
+  } else {
+    // ---- producers --------------------------------------------------------------------------
+    // activation tile: thread t stages rows t/8 + 64 j (j < 8), 16-byte chunk t%8; rows past the batch are clamped
+    // onto the last row (their accumulator columns are never stored)
+    const int prow = tid >> 3, chunk = tid & 7;
+    const uint32_t p_off = sw128_off(prow, chunk);       // rows r and r + 64 share (r & 7)
+    const float *act = kDgrad ? a.dy + (int64_t)s * a.B * a.out : a.x + (int64_t)s * a.x_sstride;
+    const float *arow[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int64_t b = n0 + prow + 64 * j;
+      if (b > a.B - 1) b = a.B - 1;
+      arow[j] = act + b * Kdim + chunk * 4;
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb % NSTG;
+      if (kb >= NSTG) mbar_wait(smem_u32(&ctl.empty[st]), (uint32_t)(((kb / NSTG) - 1) & 1));
+      uint8_t *As = tiles + st * STAGE, *Bs = As + A_BYTES;
+      const int64_t k0 = (int64_t)kb * BK;
+      const bool kc_ok = k0 + chunk * 4 < Kdim;
+      float4 xv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        xv[j] = kc_ok ? __ldg(reinterpret_cast<const float4 *>(arow[j] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!kDgrad) {
+        // W tile [128 o rows][32 k]: thread t samples the quads (row t/8 + 64 j, chunk t%8), j < 2
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int64_t o = m0 + prow + 64 * j;
+          float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (o < a.out && kc_ok) {
+            const int64_t e = o * a.in + k0 + chunk * 4;
+            Quad q;
+            load_quad(a, e, sample || lpcta, q);
+            float ep[4], w[4];
+            sample_quad(a, s, e, q, sample, ep, w);
+            wv = make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
+            if (lpcta) {
+              lp += logp_quad_fast(a.prior, w);
+              lq += -4.0f * kHalfLog2Pi - logsigma_quad_fast(q.sg) -
+                    0.5f * (ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2] + ep[3] * ep[3]);
+            }
+          }
+          *reinterpret_cast<float4 *>(As + p_off + j * 64 * 128) = wv;
+        }
+      } else {
+        // W^T tile [128 i rows][32 o]: warp w owns the i quads 2w, 2w+1; lane -> (o = lane%16 + 16 j, quad = lane/16).
+        // The global reads are coalesced along i; the K-major scatter below is bank-conflict free (8 consecutive
+        // rows x 16 columns per store instruction).
+        const int iq = 2 * warp + (lane >> 4);
+        const int64_t i = m0 + 4 * iq;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int ol = (lane & 15) + 16 * j;
+          const int64_t o = k0 + ol;
+          float w[4] = {0.f, 0.f, 0.f, 0.f};
+          if (o < a.out && i < a.in) {
+            const int64_t e = o * a.in + i;
+            Quad q;
+            load_quad(a, e, sample, q);
+            float ep[4];
+            sample_quad(a, s, e, q, sample, ep, w);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float *>(As + sw128_off(4 * iq + c, ol >> 2) + (ol & 3) * 4) = to_tf32(w[c]);
+        }
+      }
+      // activations: fp32 as they are (the tensor core reads the upper 19 bits: TF32 by truncation)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4 *>(Bs + p_off + j * 64 * 128) = relu ? relu4(xv[j]) : xv[j];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(smem_u32(&ctl.full[st]));
+    }
+
+    // ---- drain: warp w reads TMEM lanes 32 (w % 4) .. +31 (weight rows) and columns 128 (w / 4) .. +127 (batch) ----
+    mbar_wait_parked(smem_u32(&ctl.acc), 0);
+    tc_fence_after_sync();
+    const int q4 = warp & 3, cq = warp >> 2;
+    const int64_t m = m0 + q4 * 32 + lane;
+    const bool m_ok = m < Mdim;
+    float bias = 0.0f;
+    if (!kDgrad && m_ok) {
+      float sg, ep;
+      bias_elem(a, s, m, sample, lpcta, bias, sg, ep);
+      if (lpcta && cq == 0) { lp += logp_elem(a.prior, bias); lq += logq_elem(sg, ep); }
+    }
+    const float osc = (kDgrad && (a.flags & BBB_F_SCALE_DX) && a.out_scale_dev) ? __ldg(a.out_scale_dev) : 1.0f;
+    const bool preact = kDgrad && (a.flags & BBB_F_DX_PREACT);
+    float *dst = kDgrad ? a.dx + (int64_t)s * a.B * a.in : a.y + (int64_t)s * a.B * a.out;
+    const float *msk = preact ? a.x + (int64_t)s * a.x_sstride : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      const int col = cq * 128 + c0;
+      if (n0 + col >= a.B) break;                 // warp-uniform: the rest of this warp's columns are past the batch
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);
+      if (m_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int64_t b = n0 + col + j;
+          if (b < a.B) {
+            float r = kDgrad ? osc * v[j] : v[j] + bias;
+            if (preact && !(__ldg(msk + b * Mdim + m) > 0.0f)) r = 0.0f;
+            dst[b * Mdim + m] = r;
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+  }
+  pdl_launch_dependents();
+  if (kLogProb) block_sum2_atomic(lp, lq, red, a.logp + s, a.logq + s);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == PW) tmem_dealloc(tmem, 512);
+}
+
+// ==================================================================================================
+// wgrad for large batches:  G_s[o][i] = sum_b dz_s[b][o] x_s[b][i]  (M = 128 o, N = 256 i, K = the batch), then
+//   t = G - gp w R(w);  grad_mu += t;  grad_rho += sigmoid(rho) (t eps - gq / sigma)      (eps regenerated)
+// Both operands are MN-major: a [32 batch rows][128 B] slab of the row-major dz / x matrices IS an operand region
+// (SWIZZLE_128B_BASE32B, bbb_tc.cuh), so the main loop is a plain copy global -> shared with no transposes, 4 stages
+// of 32 batch rows deep, and runs at the tensor pipe's pace.  TMEM holds the accumulators of TWO samples
+// (2 x 256 columns): their K loops run back to back and the epilogue then finishes both with mu / rho / sigma loaded
+// once.  The epilogue reads TMEM directly: a thread owns one weight row o and 64 consecutive columns i.
+// ==================================================================================================
+constexpr int WN = 256;                    // i columns per CTA tile
+constexpr int WKB = 32;                    // batch rows per stage
+constexpr int WSTG = 4;
+constexpr int WREG = WKB * 128;            // one [32 rows][128 B] region
+constexpr int WA_BYTES = (BM / 32) * WREG; // dz slab: 4 regions (128 o)
+constexpr int WB_BYTES = (WN / 32) * WREG; // x slab : 8 regions (256 i)
+constexpr int WSTAGE = WA_BYTES + WB_BYTES;
+constexpr int kWgradDyn = WSTG * WSTAGE + 1024;
+
+struct WCtl {
+  uint64_t full[WSTG], empty[WSTG], acc;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(BT, 1) big_wgrad_kernel(const LinArgs a_in) {
+  extern __shared__ uint8_t dsm[];
+  __shared__ WCtl ctl;
+  __shared__ float colsum_s[2][BM];     // sum_b dz[b][o] of the two samples in flight (bias gradients)
+  LinArgs a = a_in;
+  uint8_t *tiles = align1024(dsm);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN, accum_flag = a.flags & BBB_F_ACCUM;
+  const int64_t o0 = (int64_t)blockIdx.x * BM, i0 = (int64_t)blockIdx.y * WN;
+  const bool bias_cta = blockIdx.y == 0;
+  const int nkb = (int)((a.B + WKB - 1) / WKB);
+  const int ngroups = (a.S + 1) / 2;
+
+  if (warp == PW) tmem_alloc(smem_u32(&ctl.tmem_base), 512);
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < WSTG; ++st) {
+      mbar_init(smem_u32(&ctl.full[st]), PW);
+      mbar_init(smem_u32(&ctl.empty[st]), 1);
+    }
+    mbar_init(smem_u32(&ctl.acc), 1);
+    mbar_fence_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = ctl.tmem_base;
+  pdl_wait();
+  rng_resolve(a.rng);
+  const float osc = a.out_scale_dev ? __ldg(a.out_scale_dev) : 1.0f;
+
+  if (warp == PW) {
+    // ---- MMA warp: the stage counter runs on across samples and groups ------------------------------
+    constexpr uint32_t idesc = idesc_tf32_major(BM, WN, 1, 1);
+    int it = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      const int ns = min(2, a.S - 2 * g);
+      if (lane == 0) {
+        for (int sl = 0; sl < ns; ++sl) {
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int st = it % WSTG;
+            mbar_wait_parked(smem_u32(&ctl.full[st]), (uint32_t)((it / WSTG) & 1));
+            tc_fence_after_sync();
+            const uint32_t As = smem_u32(tiles + st * WSTAGE), Bs = As + WA_BYTES;
+#pragma unroll
+            for (int k8 = 0; k8 < WKB / 8; ++k8)
+              mma_tf32(tmem + sl * WN, smem_desc_mn32(As + k8 * 1024, WREG), smem_desc_mn32(Bs + k8 * 1024, WREG), idesc,
+                       (kb == 0 && k8 == 0) ? 0u : 1u);
+            mma_commit(smem_u32(&ctl.empty[st]));
+          }
+        }
+        mma_commit(smem_u32(&ctl.acc));
+      }
+      __syncwarp();
+      // the accumulators are overwritten by the next group: the whole warp waits until the epilogue has read them
+      if (g + 1 < ngroups) {
+        asm volatile("bar.sync 2, %0;" ::"n"(BT) : "memory");
+        tc_fence_after_sync();
+      }
+    }
+  } else {
+    // ---- producers: slab copies.  dz: thread t -> batch rows t/32 + 16 h (h < 2), 16-byte chunk t%32 (4 o columns);
+    //                              x : thread t -> batch rows t/64 + 8 h (h < 4),  16-byte chunk t%64 (4 i columns)
+    const int ar = tid >> 5, ac = tid & 31, br = tid >> 6, bc = tid & 63;
+    const uint32_t a_off = (uint32_t)(ac >> 3) * WREG, b_off = (uint32_t)(bc >> 3) * WREG;
+    const int64_t ao = o0 + ac * 4, bi = i0 + bc * 4;
+    const bool ao_ok = ao < a.out, bi_ok = bi < a.in;
+    int it = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      const int s0 = 2 * g, ns = min(2, a.S - s0);
+      if (bias_cta && tid < 2 * BM) colsum_s[tid >> 7][tid & (BM - 1)] = 0.0f;
+      for (int sl = 0; sl < ns; ++sl) {
+        const float *dzs = a.dy + (int64_t)(s0 + sl) * a.B * a.out + (ao_ok ? ao : 0);
+        const float *xs = a.x + (int64_t)(s0 + sl) * a.x_sstride + (bi_ok ? bi : 0);
+        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        // slab loads of batch block kb into registers (zero outside the matrices)
+        auto load_slab = [&](int kb, float4 (&zv)[2], float4 (&xv)[4]) {
+          const int64_t b0 = (int64_t)kb * WKB;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int64_t b = b0 + ar + 16 * h;
+            const bool ok = ao_ok && b < a.B;
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(dzs + (ok ? b : 0) * a.out));
+            zv[h] = ok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int64_t b = b0 + br + 8 * h;
+            const bool ok = bi_ok && b < a.B;
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(xs + (ok ? b : 0) * a.in));
+            xv[h] = ok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        auto store_slab = [&](float4 (&zv)[2], float4 (&xv)[4]) {
+          const int st = it % WSTG;
+          if (bias_cta) {
+            bsum.x += zv[0].x + zv[1].x; bsum.y += zv[0].y + zv[1].y;
+            bsum.z += zv[0].z + zv[1].z; bsum.w += zv[0].w + zv[1].w;
+          }
+          if (it >= WSTG) mbar_wait(smem_u32(&ctl.empty[st]), (uint32_t)(((it / WSTG) - 1) & 1));
+          uint8_t *As = tiles + st * WSTAGE, *Bs = As + WA_BYTES;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            *reinterpret_cast<float4 *>(As + a_off + mn32_off(ar + 16 * h, ac & 7)) = zv[h];
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            *reinterpret_cast<float4 *>(Bs + b_off + mn32_off(br + 8 * h, bc & 7)) = relu ? relu4(xv[h]) : xv[h];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive1(smem_u32(&ctl.full[st]));
+          ++it;
+        };
+        // two register sets: the loads of block kb + 1 are in flight while block kb is written to the ring
+        float4 z0[2], x0[4], z1[2], x1[4];
+        load_slab(0, z0, x0);
+        for (int kb = 0; kb < nkb; kb += 2) {
+          if (kb + 1 < nkb) load_slab(kb + 1, z1, x1);
+          store_slab(z0, x0);
+          if (kb + 2 < nkb) load_slab(kb + 2, z0, x0);
+          if (kb + 1 < nkb) store_slab(z1, x1);
+        }
+        if (bias_cta) {
+          atomicAdd(&colsum_s[sl][ac * 4 + 0], bsum.x); atomicAdd(&colsum_s[sl][ac * 4 + 1], bsum.y);
+          atomicAdd(&colsum_s[sl][ac * 4 + 2], bsum.z); atomicAdd(&colsum_s[sl][ac * 4 + 3], bsum.w);
+        }
+      }
+      // ---- epilogue of the group: thread = weight row o (TMEM lane), 64 consecutive columns i ------------------
+      mbar_wait_parked(smem_u32(&ctl.acc), (uint32_t)(g & 1));
+      tc_fence_after_sync();
+      asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");   // colsum_s complete
+      const bool accum = accum_flag || g > 0;
+      float gps[2], gqs[2];
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        gps[sl] = sl < ns ? a.gp * (a.gp_dev ? __ldg(a.gp_dev + (s0 + sl) * a.g_dev_stride) : 1.0f) : 0.0f;
+        gqs[sl] = sl < ns ? a.gq * (a.gq_dev ? __ldg(a.gq_dev + (s0 + sl) * a.g_dev_stride) : 1.0f) : 0.0f;
+      }
+      const int q4 = warp & 3, cq = warp >> 2;
+      const int64_t o = o0 + q4 * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        const int col = cq * 64 + c0;
+        if (i0 + col >= a.in) break;                       // warp-uniform
+        float G[2][16];
+        tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, G[0]);
+        if (ns > 1) tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(WN + col), G[1]);
+        if (o < a.out) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + col + 4 * j;
+            if (i < a.in) {
+              const int64_t e = o * a.in + i;
+              Quad q;
+              load_quad(a, e, true, q);
+              float gm[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int sl = 0; sl < 2; ++sl) {
+                if (sl < ns) {
+                  float ep[4], w[4];
+                  sample_quad(a, s0 + sl, e, q, sample, ep, w);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    float t = G[sl][4 * j + c];
+                    if (gps[sl] != 0.0f) t = fmaf(-gps[sl] * w[c], prior_R_fast(a.prior, w[c]), t);
+                    gm[c] += t;
+                    gr[c] += t * ep[c] - gqs[sl] * __fdividef(1.0f, q.sg[c]);
+                  }
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < 4; ++c) gr[c] *= sigmoid_fast(q.rho[c]);
+              float4 *pm = reinterpret_cast<float4 *>(a.g_w_mu + e), *pr = reinterpret_cast<float4 *>(a.g_w_rho + e);
+              float4 om = make_float4(0.f, 0.f, 0.f, 0.f), orr = om;
+              if (accum) { om = *pm; orr = *pr; }
+              *pm = make_float4(fmaf(osc, gm[0], om.x), fmaf(osc, gm[1], om.y), fmaf(osc, gm[2], om.z), fmaf(osc, gm[3], om.w));
+              *pr = make_float4(fmaf(osc, gr[0], orr.x), fmaf(osc, gr[1], orr.y), fmaf(osc, gr[2], orr.z), fmaf(osc, gr[3], orr.w));
+            }
+          }
+        }
+      }
+      // bias gradients: column sums of dz, by the CTAs of the first i tile
+      if (bias_cta && tid < BM) {
+        const int64_t ob = o0 + tid;
+        if (ob < a.out) {
+          float gbm = 0.0f, gbr = 0.0f;
+          for (int sl = 0; sl < ns; ++sl) {
+            float bv, sg, ep;
+            bias_elem(a, s0 + sl, ob, sample, true, bv, sg, ep);
+            float t = colsum_s[sl][tid];
+            if (gps[sl] != 0.0f) t = fmaf(-gps[sl] * bv, prior_R(a.prior, bv), t);
+            gbm += t;
+            gbr += -expm1f(-sg) * (t * ep - gqs[sl] / sg);
+          }
+          a.g_b_mu[ob] = accum ? fmaf(osc, gbm, a.g_b_mu[ob]) : osc * gbm;
+          a.g_b_rho[ob] = accum ? fmaf(osc, gbr, a.g_b_rho[ob]) : osc * gbr;
+        }
+      }
+      tc_fence_before_sync();
+      if (g + 1 < ngroups) asm volatile("bar.sync 2, %0;" ::"n"(BT) : "memory");   // accumulators and colsum_s are free
+    }
+  }
+  pdl_launch_dependents();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == PW) tmem_dealloc(tmem, 512);
+}
+
+inline int cdiv_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+template <bool kDgrad, bool kLogProb>
+int launch_big(const LinArgs &a, cudaStream_t st) {
+  BBB_CHECK_CUDA(cudaFuncSetAttribute(big_kernel<kDgrad, kLogProb>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigDyn));
+  dim3 grid(cdiv_i(kDgrad ? a.in : a.out, BM), cdiv_i(a.B, NBT), (unsigned)a.S);
+  BBB_CHECK_CUDA(launch_pdl(big_kernel<kDgrad, kLogProb>, grid, dim3(BT), kBigDyn, st, a));
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+}  // namespace
+
+// Batches of at least 384 rows (3/4 of one 512-row tile) with 16-byte aligned rows; the weight matrix must be wide
+// enough for full tiles to matter (narrow heads go to bbb_head.cu); no dy mask (the network path fuses the ReLU
+// mask into the producer of dy: BBB_F_DX_PREACT)
+bool linear_big_fwd_supported(const LinArgs &a) {
+  return a.vec_in && a.B >= 384 && a.out >= 32 && a.in >= 32 && a.S >= 1;
+}
+bool linear_big_dgrad_supported(const LinArgs &a) {
+  return a.vec_in && a.vec_out && a.B >= 384 && a.out >= 32 && a.in >= 32 && a.S >= 1 && !a.mask;
+}
+
+int launch_linear_fwd_big(const LinArgs &a, cudaStream_t st) {
+  if (a.flags & BBB_F_LOGPROB) return launch_big<false, true>(a, st);
+  return launch_big<false, false>(a, st);
+}
+int launch_linear_dgrad_big(const LinArgs &a, cudaStream_t st) { return launch_big<true, false>(a, st); }
+
+// wgrad: rows of dz and x must be 16-byte multiples (slab copies), no dy mask
+bool linear_big_wgrad_supported(const LinArgs &a) {
+  return a.vec_in && a.vec_out && a.B >= 384 && a.out >= 32 && a.in >= 32 && a.S >= 1 && !a.mask && !a.adam_on;
+}
+int launch_linear_wgrad_big(const LinArgs &a, cudaStream_t st) {
+  BBB_CHECK_CUDA(cudaFuncSetAttribute(big_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradDyn));
+  dim3 grid(cdiv_i(a.out, BM), cdiv_i(a.in, WN));
+  BBB_CHECK_CUDA(launch_pdl(big_wgrad_kernel, grid, dim3(BT), kWgradDyn, st, a));
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+}  // namespace bbb

@@ -83,3 +83,47 @@ def test_tf32_large_batch_tiles():
     for a, b in zip(g0, g1):
         for ga, gb in zip(a, b):
             assert np.abs(ga - gb).max() <= RTOL_TF32 * np.abs(ga).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# batch-resident kernels (csrc/bbb_linear_big.cu): batches of >= 384 rows
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('B,d_in,d_out', [(384, 64, 64), (512, 256, 128), (700, 100, 72), (1030, 36, 200),
+                                          (4096, 512, 256)])
+def test_batch_resident_plain_gemm(B, d_in, d_out):
+    """sample=False: y = x mu^T + b through the [128 weight rows x 512 batch] TMEM tile; ragged weight-row tiles,
+    ragged batch tiles, a K tail (d_in % 32 != 0)."""
+    torch.manual_seed(B + d_in)
+    layer = bnn_b200.BayesianLinear(d_in, d_out, [-0.2, 0.2], [-5, -4], [1.0], False).to(DEV).eval()
+    layer.tf32 = True
+    x = torch.randn(B, d_in, device=DEV)
+    with torch.no_grad():
+        y = layer(x)
+    ref = (x.double() @ layer.weight_mu.double().t() + layer.bias_mu.double())
+    err = (y.double() - ref).abs().max() / ref.abs().max()
+    assert err < 2e-3, float(err)
+
+
+@pytest.mark.parametrize('B,d_in,hidden,S', [(400, 64, 96, 3), (1024, 128, 160, 2), (600, 36, 200, 1)])
+def test_batch_resident_train_step_matches_fp32_path(B, d_in, hidden, S):
+    """Forward (log-probs counted once per weight tile), dgrad (W^T sampled along i, (x > 0) mask in the drain) and
+    the wgrad epilogue regenerate the same Philox eps: TF32 path == exact fp32 path within the TF32 bound."""
+    mp = dict(input_shape=d_in, classes=10, batch_size=B, hidden_units=hidden, mode='classification',
+              mu_init=[-0.2, 0.2], rho_init=[-5, -4], prior_init=[0.5, 0, -6], mixture_prior=True)
+    torch.manual_seed(B)
+    x = torch.randn(B, d_in, device=DEV)
+    y = torch.randint(0, 10, (B,), device=DEV)
+    res = []
+    for tf32 in (False, True):
+        torch.manual_seed(0)
+        net = bnn_b200.BayesianNetwork(dict(mp, tf32=tf32)).to(DEV).train()
+        bnn_b200.manual_seed(1, 1)
+        info = net.sample_elbo(x, y, 0.3, S)
+        info[0].backward()
+        res.append(([float(v.detach()) for v in info], PC.net_grads(net)))
+    (i0, g0), (i1, g1) = res
+    np.testing.assert_allclose(i1[1:3], i0[1:3], rtol=1e-5)
+    np.testing.assert_allclose([i1[0], i1[3]], [i0[0], i0[3]], rtol=RTOL_TF32)
+    for a, b in zip(g0, g1):
+        for ga, gb in zip(a, b):
+            assert np.abs(ga - gb).max() <= RTOL_TF32 * np.abs(ga).max()

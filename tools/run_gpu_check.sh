@@ -1,8 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/t_all.log 2>&1; echo "all rc=$?"
-tail -3 gpurun_out/t_all.log
-timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_h3.json 2> gpurun_out/bench_h3.err; echo "bench rc=$?"
+timeout 600 python -m pytest tests/test_gpu_tf32.py -q -m gpu -x -k "batch_resident or large_batch" 2>&1 | tail -15
+timeout 600 python bench.py --workload wide --samples 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_big2.json 2> gpurun_out/bench_big2.err; echo "bench rc=$?"
 python -c "
-import json; d=json.loads(open('gpurun_out/bench_h3.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['e2e']['ms_per_step'])"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_h3.csv python bench.py --steps 3 --warmup 3 --eager --no-cpu-baseline > gpurun_out/ncu_h1.log 2>&1; echo "ncu rc=$?"
-python profiles/launch_summary.py gpurun_out/launches_h3.csv | grep -v Fill
+import json; d=json.loads(open('gpurun_out/bench_big2.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['step_roofline']['achieved_tflops']); [print(k, round(v['us'],1), v['launches_per_step']) for k,v in d['kernels'].items()]"
