@@ -461,6 +461,20 @@ def run_b200(args):
                     us_per_launch=us, share_of_step=kern_table[top]['share'],
                     peak_source='MEASURED_PEAKS.json hbm_gbs (measured)' if peaks else 'fallback 6650 GB/s',
                     algorithmic_bytes_per_launch=agg[top]['bytes'])
+        if args.workload == 'wide':
+            # dense 4096^3 contractions: the tensor pipe is the roof.  kind::tf32 runs at half the dense
+            # bf16 rate, so the denominator is half of the measured bf16 figure (sustained: the kernel runs inside a
+            # long step); flops of the dominant launch = 2 B in out per GEMM and sample (backward: dgrad + wgrad).
+            tag0 = top.split('[')[0]
+            inn, out = (int(v) for v in top[top.index('[') + 1:-1].split('x'))
+            gemms = 1 if 'fwd' in tag0 else 2
+            fl = 2.0 * w['B'] * inn * out * S * gemms
+            tpeak = float(peaks.get('bf16_tflops_sustained', 1386.7)) / 2
+            tach = fl / (us * 1e-6) / 1e12
+            roof = dict(kernel=top, bound='tensor', achieved=tach, peak=tpeak, unit='TFLOP/s', frac=tach / tpeak,
+                        traffic=None, us_per_launch=us, share_of_step=kern_table[top]['share'],
+                        peak_source='half of MEASURED_PEAKS.json bf16_tflops_sustained (kind::tf32 = half the dense bf16 rate)',
+                        algorithmic_flops_per_launch=fl)
 
     if rank != 0:
         if world > 1:
