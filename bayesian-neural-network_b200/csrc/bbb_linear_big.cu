@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(BT, 1) big_kernel(const LinArgs a_in) {
   if (warp == PW) {
     // ---- MMA warp ---------------------------------------------------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_tf32(BM, 256);
+      // forward: both operands K-major; dgrad: A = W^T MN-major (see the producers), B = dz K-major
+      constexpr uint32_t idesc = kDgrad ? idesc_tf32_major(BM, 256, 1, 0) : idesc_tf32(BM, 256);
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % NSTG;
         mbar_wait_parked(smem_u32(&ctl.full[st]), (uint32_t)((kb / NSTG) & 1));
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(BT, 1) big_kernel(const LinArgs a_in) {
           const uint64_t db = smem_desc_sw128(Bs + h * 256 * 128);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            mma_tf32(tmem + h * 256, da + 2u * kk, db + 2u * kk, idesc, (kb == 0 && kk == 0) ? 0u : 1u);
+            mma_tf32(tmem + h * 256, kDgrad ? smem_desc_mn32(As + kk * 1024, 4096) : da + 2u * kk, db + 2u * kk, idesc,
+                     (kb == 0 && kk == 0) ? 0u : 1u);
         }
         mma_commit(smem_u32(&ctl.empty[st]));
       }
@@ -165,26 +167,23 @@ __global__ void __launch_bounds__(BT, 1) big_kernel(const LinArgs a_in) {
           *reinterpret_cast<float4 *>(As + p_off + j * 64 * 128) = wv;
         }
       } else {
-        // W^T tile [128 i rows][32 o]: warp w owns the i quads 2w, 2w+1; lane -> (o = lane%16 + 16 j, quad = lane/16).
-        // The global reads are coalesced along i; the K-major scatter below is bank-conflict free (8 consecutive
-        // rows x 16 columns per store instruction).
-        const int iq = 2 * warp + (lane >> 4);
-        const int64_t i = m0 + 4 * iq;
+        // W^T tile as an MN-major operand: 4 regions of [32 o rows][128 B = 32 i] (SWIZZLE_128B_BASE32B), so a quad of
+        // 4 consecutive i of one weight row o is ONE 16-byte store and nothing is transposed.  Lane -> i quad (a warp
+        // reads 512 contiguous bytes of a weight row), warp w -> rows o = w and w + 16 of the k block.
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int ol = (lane & 15) + 16 * j;
-          const int64_t o = k0 + ol;
-          float w[4] = {0.f, 0.f, 0.f, 0.f};
+          const int ol = warp + 16 * j;
+          const int64_t o = k0 + ol, i = m0 + 4 * lane;
+          float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (o < a.out && i < a.in) {
             const int64_t e = o * a.in + i;
             Quad q;
             load_quad(a, e, sample, q);
-            float ep[4];
+            float ep[4], w[4];
             sample_quad(a, s, e, q, sample, ep, w);
+            wv = make_float4(to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<float *>(As + sw128_off(4 * iq + c, ol >> 2) + (ol & 3) * 4) = to_tf32(w[c]);
+          *reinterpret_cast<float4 *>(As + (lane >> 3) * 4096 + mn32_off(ol, lane & 7)) = wv;
         }
       }
       // activations: fp32 as they are (the tensor core reads the upper 19 bits: TF32 by truncation)
@@ -350,51 +349,84 @@ __global__ void __launch_bounds__(BT, 1) big_wgrad_kernel(const LinArgs a_in) {
         const float *dzs = a.dy + (int64_t)(s0 + sl) * a.B * a.out + (ao_ok ? ao : 0);
         const float *xs = a.x + (int64_t)(s0 + sl) * a.x_sstride + (bi_ok ? bi : 0);
         float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-        // slab loads of batch block kb into registers (zero outside the matrices)
-        auto load_slab = [&](int kb, float4 (&zv)[2], float4 (&xv)[4]) {
-          const int64_t b0 = (int64_t)kb * WKB;
+        // Slab copies with cp.async (global -> shared, 16 bytes, L2 only, zero fill outside the matrices), kAhead
+        // batch blocks in flight per thread: no registers are staged, so the latency of streaming dz and x (together
+        // as large as the L2: every wave of tiles reads them from HBM again) hides behind three slabs of copies.
+        // ReLU and the bias column sums are applied to the thread's own chunks once they have landed.
+        constexpr int kAhead = WSTG - 1;
+        // per-thread constants of the copy: the six shared-memory offsets inside a stage and the six global row
+        // pointers of batch block 0 (columns outside the matrix: pointer clamped, zero bytes copied); a block
+        // advances every pointer by 32 rows, so the loop carries no index arithmetic
+        uint32_t zoff[2], xoff[4];
+        const float *zp[2], *xp[4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int64_t b = b0 + ar + 16 * h;
-            const bool ok = ao_ok && b < a.B;
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(dzs + (ok ? b : 0) * a.out));
-            zv[h] = ok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h = 0; h < 2; ++h) {
+          zoff[h] = a_off + mn32_off(ar + 16 * h, ac & 7);
+          zp[h] = dzs + (int64_t)(ar + 16 * h) * a.out;
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          xoff[h] = WA_BYTES + b_off + mn32_off(br + 8 * h, bc & 7);
+          xp[h] = xs + (int64_t)(br + 8 * h) * a.in;
+        }
+        const int64_t zstep = (int64_t)WKB * a.out, xstep = (int64_t)WKB * a.in;
+        const uint32_t ring = smem_u32(tiles);
+        auto issue_slab = [&](int kb, int j) {      // j: running stage index of that slab; called for kb = 0, 1, 2, ...
+          const int st = j % WSTG;
+          if (j >= WSTG) mbar_wait(smem_u32(&ctl.empty[st]), (uint32_t)(((j / WSTG) - 1) & 1));
+          const uint32_t base = ring + st * WSTAGE;
+          if ((int64_t)(kb + 1) * WKB <= a.B) {     // whole block inside the batch: the common case
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + zoff[h]), "l"(zp[h]), "r"(ao_ok ? 16 : 0) : "memory");
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + xoff[h]), "l"(xp[h]), "r"(bi_ok ? 16 : 0) : "memory");
+          } else {                                   // last, partial block: rows past the batch are zero-filled
+            const int64_t b0 = (int64_t)kb * WKB;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const bool ok = ao_ok && b0 + ar + 16 * h < a.B;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + zoff[h]), "l"(ok ? zp[h] : dzs), "r"(ok ? 16 : 0) : "memory");
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const bool ok = bi_ok && b0 + br + 8 * h < a.B;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + xoff[h]), "l"(ok ? xp[h] : xs), "r"(ok ? 16 : 0) : "memory");
+            }
           }
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int64_t b = b0 + br + 8 * h;
-            const bool ok = bi_ok && b < a.B;
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(xs + (ok ? b : 0) * a.in));
-            xv[h] = ok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int h = 0; h < 2; ++h) zp[h] += zstep;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) xp[h] += xstep;
         };
-        auto store_slab = [&](float4 (&zv)[2], float4 (&xv)[4]) {
+        for (int p = 0; p < kAhead; ++p) {
+          if (p < nkb) issue_slab(p, it + p);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          if (kb + kAhead < nkb) issue_slab(kb + kAhead, it + kAhead);
+          asm volatile("cp.async.commit_group;" ::: "memory");      // (an empty group keeps the count uniform)
+          asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");   // this thread's copies of block kb landed
           const int st = it % WSTG;
+          uint8_t *stage = tiles + st * WSTAGE;
           if (bias_cta) {
-            bsum.x += zv[0].x + zv[1].x; bsum.y += zv[0].y + zv[1].y;
-            bsum.z += zv[0].z + zv[1].z; bsum.w += zv[0].w + zv[1].w;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 z = *reinterpret_cast<const float4 *>(stage + zoff[h]);
+              bsum.x += z.x; bsum.y += z.y; bsum.z += z.z; bsum.w += z.w;
+            }
           }
-          if (it >= WSTG) mbar_wait(smem_u32(&ctl.empty[st]), (uint32_t)(((it / WSTG) - 1) & 1));
-          uint8_t *As = tiles + st * WSTAGE, *Bs = As + WA_BYTES;
+          if (relu) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            *reinterpret_cast<float4 *>(As + a_off + mn32_off(ar + 16 * h, ac & 7)) = zv[h];
-#pragma unroll
-          for (int h = 0; h < 4; ++h)
-            *reinterpret_cast<float4 *>(Bs + b_off + mn32_off(br + 8 * h, bc & 7)) = relu ? relu4(xv[h]) : xv[h];
+            for (int h = 0; h < 4; ++h) {
+              float4 *px = reinterpret_cast<float4 *>(stage + xoff[h]);
+              *px = relu4(*px);
+            }
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive1(smem_u32(&ctl.full[st]));
-          ++it;
-        };
-        // two register sets: the loads of block kb + 1 are in flight while block kb is written to the ring
-        float4 z0[2], x0[4], z1[2], x1[4];
-        load_slab(0, z0, x0);
-        for (int kb = 0; kb < nkb; kb += 2) {
-          if (kb + 1 < nkb) load_slab(kb + 1, z1, x1);
-          store_slab(z0, x0);
-          if (kb + 2 < nkb) load_slab(kb + 2, z0, x0);
-          if (kb + 1 < nkb) store_slab(z1, x1);
         }
         if (bias_cta) {
           atomicAdd(&colsum_s[sl][ac * 4 + 0], bsum.x); atomicAdd(&colsum_s[sl][ac * 4 + 1], bsum.y);

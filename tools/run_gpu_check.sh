@@ -1,9 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/bench_n2c.json 2> gpurun_out/bench_n2c.err; echo "rc=$?"
-tail -1 gpurun_out/bench_n2c.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'])"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload wide --samples 4 --steps 3 --warmup 3 > gpurun_out/bench_n2w.json 2> gpurun_out/bench_n2w.err; echo "rc=$?"
-tail -1 gpurun_out/bench_n2w.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['n_gpus'], d['ms_per_step'], d['value'], d['step_roofline']['achieved_tflops'], d['roofline'])"
-timeout 300 python bench.py --workload wide --samples 4 --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['n_gpus'], d['ms_per_step'], d['value'], d['step_roofline']['achieved_tflops'], d['roofline'])"
+timeout 180 python -m pytest tests/test_gpu_tf32.py -q -m gpu -x -k "batch_resident or large_batch" 2>&1 | tail -3
+timeout 180 python bench.py --workload wide --samples 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_big4.json 2> gpurun_out/bench_big4.err; echo "bench rc=$?"
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_big4.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['step_roofline']['achieved_tflops'], d['roofline']['frac']); [print(k, round(v['us'],1), v['launches_per_step']) for k,v in d['kernels'].items()]"
