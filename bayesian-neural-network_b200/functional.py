@@ -179,15 +179,28 @@ def _ws_head(x, x_stride, p, eps, l, prior, S, B, flags, y, logp, logq, mode, ta
                                  beta_h, L.ptr(beta_d), L.ptr(out4), L.ptr(done), L.stream()), 'bbb_head_fwd')
 
 
+def _prezero(B):
+    """Only the kernels for batches of at most 128 rows combine split-K partial tiles with red.add into a zero-filled
+    output (BBB_F_OUT_ZEROED).  Above that every kernel either writes its output with plain stores or zeroes it
+    itself, so the per-step workspace (gigabytes at batch 4096) is allocated uninitialised."""
+    return B <= 128
+
+
+def _workspace(shapes, device, zero):
+    if zero:
+        return _zeroed_views(shapes, device)
+    return [torch.empty(sh, dtype=torch.float32, device=device) for sh in shapes]
+
+
 def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq, ys=None, head=None):
     """All layers, all S samples.  Returns the list of pre-activation outputs ys[l] = [S,B,out_l]
     (written into the zero-filled `ys` when the caller supplies them).  `head(inp, stride, flags, y)`, when given,
     runs the last layer instead of bbb_linear_fwd (the fused ELBO tail)."""
     B = x2.shape[0]
     base = ((L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if logprob else 0) | (L.F_TF32 if tf32 else 0) |
-            L.F_OUT_ZEROED)
+            (L.F_OUT_ZEROED if _prezero(B) else 0))
     if ys is None:
-        ys = _zeroed_views([(S, B, p[0].shape[0]) for p in params], x2.device)
+        ys = _workspace([(S, B, p[0].shape[0]) for p in params], x2.device, _prezero(B))
     inp, stride = x2, 0
     for l, p in enumerate(params):
         out, inn = p[0].shape
@@ -206,12 +219,12 @@ def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq,
     hands down the gradient w.r.t. the PRE-activation output of the layer below (BBB_F_DX_PREACT: the ReLU mask
     is applied where dx is produced), so no layer needs a separate mask pass over dy."""
     B = x2.shape[0]
-    base = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0) | L.F_OUT_ZEROED
+    base = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0) | (L.F_OUT_ZEROED if _prezero(B) else 0)
     grads = _alloc_grads(params) if fused_opt is None else [None] * len(params)
     dy, dx0 = d_out, None
     first = 0 if need_dx0 else 1
     if dxs is None:
-        dxs = [None] * first + _zeroed_views([(S, B, p[0].shape[1]) for p in params[first:]], x2.device)
+        dxs = [None] * first + _workspace([(S, B, p[0].shape[1]) for p in params[first:]], x2.device, _prezero(B))
     for l in reversed(range(len(params))):
         p = params[l]
         out, inn = p[0].shape
@@ -347,7 +360,10 @@ class _FusedELBO(torch.autograd.Function):
         shapes = [(2 * (2 * S + 1) + 2,)] + [(S, B, p[0].shape[0]) for p in params]
         if need_grad:
             shapes += [(S, B, p[0].shape[1]) for p in params[1:]]
-        ws = _zeroed_views(shapes, dev)
+        if _prezero(B):
+            ws = _zeroed_views(shapes, dev)
+        else:                      # large batch: only the accumulators are zeroed
+            ws = _zeroed_views(shapes[:1], dev) + _workspace(shapes[1:], dev, False)
         acc = ws[0][:2 * (2 * S + 1)].view(torch.float64)
         done = ws[0][2 * (2 * S + 1):]
         ys, dxs = ws[1:1 + len(params)], ([None] + ws[1 + len(params):] if need_grad else None)

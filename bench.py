@@ -461,6 +461,13 @@ def run_b200(args):
                     us_per_launch=us, share_of_step=kern_table[top]['share'],
                     peak_source='MEASURED_PEAKS.json hbm_gbs (measured)' if peaks else 'fallback 6650 GB/s',
                     algorithmic_bytes_per_launch=agg[top]['bytes'])
+        try:      # DRAM bytes of the same kernel from the committed ncu --set full capture (per launch), if present
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+            if args.workload == 'mnist' and top in tr['kernels']:
+                roof['traffic'] = tr['kernels'][top]['dram_bytes']
+                roof['traffic_source'] = 'profiles/r1_traffic.json (' + tr['kernels'][top]['kernel'] + ')'
+        except Exception:
+            pass
         if args.workload == 'wide':
             # dense 4096^3 contractions: the tensor pipe is the roof.  kind::tf32 runs at half the dense
             # bf16 rate, so the denominator is half of the measured bf16 figure (sustained: the kernel runs inside a

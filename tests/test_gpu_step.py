@@ -51,29 +51,40 @@ def test_graphed_step_equals_eager_steps(name, tf32):
         info = gs(x, y, beta=c.beta)
         losses_g.append(float(info[0]))
 
-    net_e = PC.build_net(c, DEV, tf32=tf32).train()
-    opt_e = bnn_b200.FusedAdam(net_e.parameters(), lr=1e-3)
-    bnn_b200.manual_seed(seed, step0 + warm)          # the capture consumed `warm` + 1 host steps; it baked step0 + warm
-    losses_e = []
-    elbo = net_e.sample_elbo_lr if c.lr else net_e.sample_elbo
-    for k in range(3):
-        net_e.zero_grad()
-        info = elbo(x, y, c.beta, c.S, sigma=c.sigma)
-        info[0].backward()
-        opt_e.step()
-        losses_e.append(float(info[0].detach()))
+    def eager_run():
+        net_e = PC.build_net(c, DEV, tf32=tf32).train()
+        opt_e = bnn_b200.FusedAdam(net_e.parameters(), lr=1e-3)
+        bnn_b200.manual_seed(seed, step0 + warm)      # the capture consumed `warm` + 1 host steps; it baked step0 + warm
+        losses = []
+        elbo = net_e.sample_elbo_lr if c.lr else net_e.sample_elbo
+        for k in range(3):
+            net_e.zero_grad()
+            info = elbo(x, y, c.beta, c.S, sigma=c.sigma)
+            info[0].backward()
+            opt_e.step()
+            losses.append(float(info[0].detach()))
+        return net_e, losses
+
+    net_e, losses_e = eager_run()
     np.testing.assert_allclose(losses_g, losses_e, rtol=1e-5 if not tf32 else 1e-4)
-    for p, q in zip(net_g.parameters(), net_e.parameters()):
-        if not tf32:
+    if not tf32:
+        for p, q in zip(net_g.parameters(), net_e.parameters()):
             assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), float((p - q).abs().max())
-        else:
-            # The tensor-core kernels combine split-K partial tiles with fp32 red.add, whose order varies from run
-            # to run (~1e-7), and the next TF32 rounding of those activations turns a fraction of that into ~1e-5
-            # relative differences (measured eager-vs-eager with identical seeds, tools/debug_graph.py).  Adam's
-            # first steps move a weight by +-lr whatever its gradient's size, so weights with a tiny gradient can
-            # step the other way.  Two runs of this path agree statistically, not bit for bit.
-            bad = ~torch.isclose(p, q, rtol=1e-4, atol=2e-6)
-            assert bad.float().mean() <= 0.03, float(bad.float().mean())
+    else:
+        # The tensor-core kernels combine split-K partial tiles with fp32 red.add, whose order varies from run
+        # to run (~1e-7), and the next TF32 rounding of those activations turns a fraction of that into ~1e-5
+        # relative differences (measured eager-vs-eager with identical seeds, tools/debug_graph.py).  Adam's
+        # first steps move a weight by +-lr whatever its gradient's size, so weights with a tiny gradient can
+        # step the other way.  Two runs of this path agree statistically, not bit for bit -- so the bound on
+        # graph-vs-eager is set by the eager-vs-eager disagreement measured here, in the same process.
+        net_e2, _ = eager_run()
+
+        def mismatch(pa, pb):
+            return float((~torch.isclose(pa, pb, rtol=1e-4, atol=2e-6)).float().mean())
+        for p, q, q2 in zip(net_g.parameters(), net_e.parameters(), net_e2.parameters()):
+            floor = mismatch(q, q2)
+            got = mismatch(p, q)
+            assert got <= max(0.03, 3 * floor + 0.01), (got, floor)
             assert float((p - q).abs().max()) <= 3 * 2 * 1e-3 * 1.05
     assert losses_g[0] != losses_g[1]                   # fresh eps every replay
 
@@ -84,7 +95,7 @@ def test_fused_optimizer_matches_separate_adam_on_gpu():
     c = Case('cfg2_mnist_mix')
     x, y = c.x.to(DEV), c.y.to(DEV)
     res = []
-    for fuse in (False, True):
+    for fuse in (False, True, False):          # the second unfused run measures this path's run-to-run noise
         net = PC.build_net(c, DEV, tf32=True).train()
         opt = bnn_b200.FusedAdam(net.parameters(), lr=1e-3)
         if fuse:
@@ -96,10 +107,15 @@ def test_fused_optimizer_matches_separate_adam_on_gpu():
         opt.step()
         res.append(([p.detach().clone() for p in net.parameters()],
                     [opt.state[p]['exp_avg_sq'].clone() for p in net.parameters()]))
-    for a, b in zip(res[0][0], res[1][0]):
-        bad = ~torch.isclose(a, b, rtol=1e-5, atol=1e-7)
-        assert bad.float().mean() <= 1e-3, float(bad.float().mean())      # sign flips of round-off-sized gradients
+
+    def mismatch(pa, pb, rtol, atol):
+        return float((~torch.isclose(pa, pb, rtol=rtol, atol=atol)).float().mean())
+    for a, b, a2 in zip(res[0][0], res[1][0], res[2][0]):
+        floor = mismatch(a, a2, 1e-5, 1e-7)
+        got = mismatch(a, b, 1e-5, 1e-7)
+        assert got <= max(1e-3, 3 * floor + 1e-3), (got, floor)   # sign flips of round-off-sized gradients
         assert float((a - b).abs().max()) <= 2 * 1e-3 * 1.01
-    for a, b in zip(res[0][1], res[1][1]):
-        bad = ~torch.isclose(a, b, rtol=2e-2, atol=1e-10)                   # v = (1-b2) g^2: the gradients agree
-        assert bad.float().mean() <= 0.05, float(bad.float().mean())         # (up to the TF32 path's reorder noise)
+    for a, b, a2 in zip(res[0][1], res[1][1], res[2][1]):
+        floor = mismatch(a, a2, 2e-2, 1e-10)
+        got = mismatch(a, b, 2e-2, 1e-10)                          # v = (1-b2) g^2: the gradients agree
+        assert got <= max(0.05, 3 * floor + 0.01), (got, floor)    # (up to the TF32 path's reorder noise)

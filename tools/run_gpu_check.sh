@@ -1,5 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 180 python -m pytest tests/test_gpu_tf32.py -q -m gpu -x -k "batch_resident or large_batch" 2>&1 | tail -3
-timeout 180 python bench.py --workload wide --samples 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_big4.json 2> gpurun_out/bench_big4.err; echo "bench rc=$?"
+timeout 300 python -m pytest tests/test_gpu_tf32.py tests/test_gpu_head.py -q -m gpu 2>&1 | tail -2
+timeout 180 python bench.py --workload wide --samples 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_big5.json 2> gpurun_out/bench_big5.err; echo "bench rc=$?"
 python -c "
-import json; d=json.loads(open('gpurun_out/bench_big4.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['step_roofline']['achieved_tflops'], d['roofline']['frac']); [print(k, round(v['us'],1), v['launches_per_step']) for k,v in d['kernels'].items()]"
+import json; d=json.loads(open('gpurun_out/bench_big5.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['step_roofline']['achieved_tflops'], d['roofline']['frac'], d['e2e'])"
+timeout 300 python bench.py --workload wide --samples 8 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_big6.json 2> gpurun_out/bench_big6.err; echo "bench rc=$?"
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_big6.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['step_roofline']['achieved_tflops'], d['roofline']['frac'], d['e2e'])"
