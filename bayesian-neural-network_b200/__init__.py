@@ -6,9 +6,9 @@ from . import _lib, rng, functional, parallel
 from .rng import set_eps_mode, get_eps_mode, manual_seed, eps_mode, set_sample_base, use_device_step
 from .layers import ScaleMixtureGaussian, GaussianNode, BayesianLinear, BayesianLinearLR
 from .network import BayesianNetwork, MLP, MLP_Dropout
-from .optim import FusedAdam
+from .optim import FusedAdam, PeerShardedAdam
 from .graphed import GraphedTrainStep
 
 __all__ = ['ScaleMixtureGaussian', 'GaussianNode', 'BayesianLinear', 'BayesianLinearLR', 'BayesianNetwork',
            'MLP', 'MLP_Dropout', 'set_eps_mode', 'get_eps_mode', 'manual_seed', 'eps_mode', 'set_sample_base',
-           'use_device_step', 'functional', 'rng', 'parallel', 'FusedAdam', 'GraphedTrainStep']
+           'use_device_step', 'functional', 'rng', 'parallel', 'FusedAdam', 'PeerShardedAdam', 'GraphedTrainStep']

@@ -31,6 +31,12 @@ class AdamFuse(C.Structure):
                 ('step_dev', C.c_void_p), ('lr_scale_dev', C.c_void_p)]
 
 
+class PeerComm(C.Structure):
+    """struct bbb_peer_comm: every rank's gradient bucket / parameter buffer / flag words as mapped in this process"""
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('grads', C.c_void_p * 8), ('params', C.c_void_p * 8),
+                ('flags', C.c_void_p * 8), ('epoch', C.c_void_p), ('done_blocks', C.c_void_p)]
+
+
 P, I64, I32, F32, F64, U32, U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_double, C.c_uint32, C.c_uint64
 _SIGS = {
     'bbb_version': ([], C.c_int),
@@ -53,6 +59,9 @@ _SIGS = {
                       P, P, P, P], C.c_int),
     'bbb_elbo_finalize': ([P, P, P, P, I64, F32, P, P, P], C.c_int),
     'bbb_adam_step': ([I32, P, P, P, P, P, F64, F64, F64, F64, U32, P, P, P], C.c_int),
+    'bbb_enable_peer_access': ([I32], C.c_int),
+    'bbb_ipc_open': ([C.c_char_p, I64, P], C.c_int),
+    'bbb_adam_step_peer': ([P, P, P, I64, F64, F64, F64, F64, U32, P, P, P], C.c_int),
     'bbb_counter_add': ([P, U32, P], C.c_int),
 }
 EXPORTS = tuple(_SIGS)

@@ -4,6 +4,8 @@
 // parameter (p, g, m, v in; p, m, v out), 16-byte vector accesses, grid = a multiple of the 148 SMs.
 // The update rule is exactly torch's (non-amsgrad, no weight decay):
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+#include <string.h>
+
 #include "bbb_common.cuh"
 
 namespace bbb {
@@ -61,10 +63,178 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   }
 }
 
+// ==================================================================================================
+// Multi-GPU step: gradient reduce-scatter + Adam + parameter all-gather in ONE kernel over NVLink peer memory.
+// Rank r owns the slice [r n/W, (r+1) n/W) of the flat parameter space.  For its slice it sums the W ranks' gradient
+// buckets (peer loads, fixed rank order), applies the Adam update with its local m / v, and stores the new
+// parameters into every rank's parameter buffer (peer stores).  Two flag barriers in peer memory bracket it:
+//   entry: every rank's gradients are complete (its backward has finished) before anyone reads them;
+//   exit : every rank has finished reading my gradients and writing my parameters before my kernel completes,
+//          so the next step on this stream may overwrite the bucket and read the parameters.
+// Flags are monotonically increasing call counts (never reset).  No NCCL, no extra launch, no extra pass over the
+// gradients; each rank touches 1/W of the optimiser state.
+// ==================================================================================================
+struct PeerArgs {
+  int world, rank;
+  const float *g[BBB_MAX_PEERS];
+  float *p[BBB_MAX_PEERS];
+  uint32_t *flags[BBB_MAX_PEERS];
+  uint32_t *epoch, *done;
+  float *m, *v;
+  int64_t n;
+  double lr, b1, b2;
+  float eps;
+  uint32_t step;
+  const uint32_t *step_dev;
+  const float *lr_scale_dev;
+};
+
+__device__ __forceinline__ void st_flag_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();                         // this rank's backward (the previous kernels of the stream) is complete
+  __shared__ AdamConst cs;
+  __shared__ uint32_t last_s;
+  const int W = a.world, tid = threadIdx.x;
+  const uint32_t e = *reinterpret_cast<volatile uint32_t *>(a.epoch) + 1u;   // this call's number (same in every block)
+  if (tid == 0) cs = adam_consts(a.lr, a.b1, a.b2, a.eps, a.step, a.step_dev, a.lr_scale_dev);
+  // ---- entry barrier: block 0 announces this rank, every block waits for all ranks
+  if (blockIdx.x == 0 && tid < W) {
+    __threadfence_system();
+    st_flag_sys(a.flags[tid] + a.rank, e);
+  }
+  if (tid < W) {
+    const uint32_t *f = a.flags[a.rank] + tid;
+    while ((int32_t)(ld_flag_sys(f) - e) < 0) __nanosleep(20);
+  }
+  __syncthreads();
+  const AdamConst c = cs;
+  const float inv_w = 1.0f / (float)W;
+  // ---- this rank's slice, in 16-byte quads; the last rank also takes the n % 4 tail
+  const int64_t nq = a.n >> 2;
+  const int64_t q_lo = nq * a.rank / W, q_hi = nq * (a.rank + 1) / W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = q_lo + (int64_t)blockIdx.x * blockDim.x + tid; q < q_hi; q += stride) {
+    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < BBB_MAX_PEERS; ++k) {
+      if (k < W) {
+        const float4 t = __ldcg(reinterpret_cast<const float4 *>(a.g[k]) + q);   // peer memory: never through L1
+        G.x += t.x; G.y += t.y; G.z += t.z; G.w += t.w;
+      }
+    }
+    G.x *= inv_w; G.y *= inv_w; G.z *= inv_w; G.w *= inv_w;
+    float4 P = reinterpret_cast<const float4 *>(a.p[a.rank])[q];
+    float4 M = reinterpret_cast<const float4 *>(a.m)[q], V = reinterpret_cast<const float4 *>(a.v)[q];
+    adam1(P.x, G.x, M.x, V.x, c);
+    adam1(P.y, G.y, M.y, V.y, c);
+    adam1(P.z, G.z, M.z, V.z, c);
+    adam1(P.w, G.w, M.w, V.w, c);
+    reinterpret_cast<float4 *>(a.m)[q] = M;
+    reinterpret_cast<float4 *>(a.v)[q] = V;
+#pragma unroll
+    for (int k = 0; k < BBB_MAX_PEERS; ++k)
+      if (k < W) reinterpret_cast<float4 *>(a.p[k])[q] = P;
+  }
+  if (a.rank == W - 1 && blockIdx.x == 0 && tid < (a.n & 3)) {
+    const int64_t i = (nq << 2) + tid;
+    float G = 0.0f;
+    for (int k = 0; k < W; ++k) G += __ldcg(a.g[k] + i);
+    G *= inv_w;
+    float P = a.p[a.rank][i], M = a.m[i], V = a.v[i];
+    adam1(P, G, M, V, c);
+    a.m[i] = M; a.v[i] = V;
+    for (int k = 0; k < W; ++k) a.p[k][i] = P;
+  }
+  // ---- exit barrier: the last block to finish announces this rank and waits for the others
+  __threadfence_system();             // this thread's peer stores are performed
+  __syncthreads();
+  if (tid == 0) last_s = atomicAdd(a.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (last_s) {
+    if (tid < W) {
+      __threadfence_system();
+      st_flag_sys(a.flags[tid] + W + a.rank, e);
+      const uint32_t *f = a.flags[a.rank] + W + tid;
+      while ((int32_t)(ld_flag_sys(f) - e) < 0) __nanosleep(20);
+    }
+    __syncthreads();
+    if (tid == 0) { *a.done = 0u; *a.epoch = e; }
+  }
+}
+
 }  // namespace
 }  // namespace bbb
 
 using namespace bbb;
+
+extern "C" int bbb_enable_peer_access(int32_t peer_device) {
+  int cur = -1;
+  BBB_CHECK_CUDA(cudaGetDevice(&cur));
+  if (cur == peer_device) return BBB_OK;
+  int can = 0;
+  BBB_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  if (!can) return fail(BBB_EUNSUPPORTED, "bbb_enable_peer_access: device %d cannot access device %d", cur, peer_device);
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return BBB_OK; }
+  BBB_CHECK_CUDA(e);
+  return BBB_OK;
+}
+
+extern "C" int bbb_ipc_open(const void *handle, int64_t offset_bytes, void **out_ptr) {
+  BBB_CHECK_ARG(handle && out_ptr && offset_bytes >= 0, "null pointer or negative offset");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void *base = nullptr;
+  // opened with the CALLER's device current: the mapping is then usable by that device's kernels (peer access to
+  // the exporting device is enabled on demand)
+  BBB_CHECK_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *out_ptr = static_cast<char *>(base) + offset_bytes;
+  return BBB_OK;
+}
+
+extern "C" int bbb_adam_step_peer(const bbb_peer_comm *comm, float *exp_avg, float *exp_avg_sq, int64_t n, double lr,
+                                  double beta1, double beta2, double eps, uint32_t step, const uint32_t *step_dev,
+                                  const float *lr_scale_dev, void *stream) {
+  BBB_CHECK_ARG(comm && exp_avg && exp_avg_sq, "null pointer");
+  BBB_CHECK_ARG(comm->world >= 1 && comm->world <= BBB_MAX_PEERS && comm->rank >= 0 && comm->rank < comm->world,
+                "1 <= world <= 8, 0 <= rank < world");
+  BBB_CHECK_ARG(comm->epoch && comm->done_blocks, "null epoch / counter word");
+  BBB_CHECK_ARG(n >= 0, "negative size");
+  BBB_CHECK_ARG(step + (step_dev ? 1u : 0u) >= 1u, "Adam step is 1-based");
+  PeerArgs a{};
+  a.world = comm->world; a.rank = comm->rank;
+  for (int k = 0; k < comm->world; ++k) {
+    BBB_CHECK_ARG(comm->grads[k] && comm->params[k] && comm->flags[k], "null peer pointer");
+    BBB_CHECK_ARG(((reinterpret_cast<uintptr_t>(comm->grads[k]) | reinterpret_cast<uintptr_t>(comm->params[k])) & 15u) == 0,
+                  "peer buffers must be 16-byte aligned");
+    a.g[k] = comm->grads[k]; a.p[k] = comm->params[k]; a.flags[k] = comm->flags[k];
+  }
+  BBB_CHECK_ARG(((reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u) == 0,
+                "optimiser state must be 16-byte aligned");
+  a.epoch = comm->epoch; a.done = comm->done_blocks;
+  a.m = exp_avg; a.v = exp_avg_sq; a.n = n;
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = (float)eps; a.step = step; a.step_dev = step_dev;
+  a.lr_scale_dev = lr_scale_dev;
+  // every block must be able to run while block 0 is still waiting at the entry barrier, and the grid of every rank
+  // must make progress independently: at most 4 blocks per SM, so the grid is always co-resident
+  const int64_t slice_q = (n >> 2) / comm->world + 1;
+  int64_t blocks = (slice_q + 255) / 256;
+  const int64_t cap = (int64_t)kSMs * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  BBB_CHECK_CUDA(launch_pdl(peer_adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a));
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
 
 extern "C" int bbb_adam_step(int32_t n_tensors, float *const *params, const float *const *grads, float *const *exp_avg,
                              float *const *exp_avg_sq, const int64_t *sizes, double lr, double beta1, double beta2,

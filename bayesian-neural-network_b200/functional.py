@@ -42,11 +42,19 @@ def _f32c(t):
 grad_ready_hook = None
 
 
+# A persistent flat gradient bucket (optim.PeerShardedAdam installs one that the other ranks can read over NVLink):
+# when set and large enough, the network-level backward writes its gradients there instead of a fresh allocation.
+grad_bucket = None
+
+
 def _alloc_grads(params):
     """Gradient buffers for every layer as consecutive views of ONE flat tensor, in parameter order, so a
     multi-GPU step can all-reduce them with a single collective and no copies (parallel.py)."""
     total = sum(t.numel() for p in params for t in p)
-    flat = torch.empty(total, dtype=torch.float32, device=params[0][0].device)
+    if grad_bucket is not None and grad_bucket.numel() >= total and grad_bucket.device == params[0][0].device:
+        flat = grad_bucket[:total]
+    else:
+        flat = torch.empty(total, dtype=torch.float32, device=params[0][0].device)
     out, off = [], 0
     for p in params:
         g, start = [], off

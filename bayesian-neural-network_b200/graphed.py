@@ -25,7 +25,8 @@ class GraphedTrainStep:
         self.beta = torch.full((1,), float(beta), dtype=torch.float32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)      # read as uint32 by the kernels
         self._elbo = net.sample_elbo_lr if net.local_reparam else net.sample_elbo
-        self._ar = parallel.OverlappedAllReduce(world_size)
+        # an optimiser that exchanges the gradients itself (PeerShardedAdam) needs no all-reduce around the backward
+        self._ar = parallel.OverlappedAllReduce(1 if getattr(optimizer, 'reduces_gradients', False) else world_size)
         if hasattr(optimizer, 'use_device_step'):
             optimizer.use_device_step(self.counter)
         # Opt-in, one GPU: the optimiser's update rides in the backward kernels' gradient epilogue (no gradient round

@@ -73,3 +73,133 @@ class FusedAdam(torch.optim.Optimizer):
         L.check(L.lib().bbb_adam_step(n, tabs[0], tabs[1], tabs[2], tabs[3], sizes, float(group['lr']), float(b1),
                                       float(b2), float(group['eps']), self._t, L.ptr(self.step_dev),
                                       L.ptr(self.lr_scale_dev), L.stream()), 'bbb_adam_step')
+
+
+_ipc_bases = {}     # CUDA IPC handle bytes -> base pointer mapped in this process (a handle is opened once)
+
+
+def open_peers(t, group=None):
+    """Map the same tensor of every rank of `group` (one node) into this process.  The exporter's handle comes from
+    torch (`_share_cuda_`: handle of the cudaMalloc block + byte offset of the tensor inside it); it is opened by
+    bbb_ipc_open with THIS rank's device current, so that this device's kernels can load / store it over NVLink.
+    Returns the device pointers [rank 0's tensor, rank 1's, ...] as ints (this rank's own: t.data_ptr())."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    shared = t.untyped_storage()._share_cuda_()       # (device, handle, size, offset, ...)
+    handle = bytes(shared[1])
+    # torch prefixes the 64-byte cudaIpcMemHandle_t with a version / type tag ('c' = plain cudaMalloc block)
+    prefix, handle = handle[:-64], handle[-64:]
+    if len(handle) != 64 or (prefix and prefix[-1:] != b'c'):
+        raise RuntimeError(f'PeerShardedAdam needs cudaMalloc-backed tensors: unexpected CUDA IPC handle '
+                           f'(prefix {prefix!r}, {len(handle)} bytes); expandable segments are not shareable here')
+    mine = (int(shared[0]), handle, int(shared[3]) + t.storage_offset() * t.element_size())
+    every = [None] * world
+    dist.all_gather_object(every, mine, group=group)
+    ptrs = []
+    with torch.cuda.device(t.device):
+        for k, (dev_k, handle, off) in enumerate(every):
+            if k == rank:
+                ptrs.append(t.data_ptr())
+                continue
+            L.check(L.lib().bbb_enable_peer_access(dev_k), 'bbb_enable_peer_access')
+            if handle not in _ipc_bases:
+                out = C.c_void_p()
+                L.check(L.lib().bbb_ipc_open(handle, 0, C.byref(out)), 'bbb_ipc_open')
+                _ipc_bases[handle] = out.value
+            ptrs.append(_ipc_bases[handle] + off)
+    return ptrs
+
+
+class PeerShardedAdam(torch.optim.Optimizer):
+    """Data-parallel Adam whose gradient exchange rides in the optimiser kernel (csrc/bbb_adam.cu:
+    bbb_adam_step_peer): gradient reduce-scatter + Adam + parameter all-gather in ONE launch over NVLink peer
+    memory.  Replaces `all_reduce(grads); optimizer.step()`: there is no NCCL call in the step, no separate pass
+    over the gradients, and each rank touches 1/world of the optimiser state.
+
+    The parameters are re-homed into one flat buffer (their `.data` become views of it, same values, same
+    layout) and the network-level backward writes its gradients into one flat bucket (functional.grad_bucket);
+    both are opened by every rank of the node through CUDA IPC.  Every rank must call step() once per step.
+    Same update rule and state names as torch.optim.Adam (the per-parameter `exp_avg` / `exp_avg_sq` are views of the
+    flat state; only this rank's slice of them is ever non-zero)."""
+
+    reduces_gradients = True      # callers must NOT all-reduce the gradients themselves
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, group=None):
+        import torch.distributed as dist
+        from . import functional as F
+        params = list(params)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        for p in params:
+            L.require_cuda(p)
+            if not (p.is_contiguous() and p.dtype == torch.float32):
+                raise RuntimeError('PeerShardedAdam needs contiguous fp32 parameters')
+        self.group = group
+        multi = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        if self.world > 8:
+            raise RuntimeError('PeerShardedAdam: at most 8 ranks (one NVLink node)')
+        dev = params[0].device
+        self.n = sum(p.numel() for p in params)
+        npad = (self.n + 3) // 4 * 4
+        self.flat_p = torch.zeros(npad, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(npad, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(npad, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(npad, dtype=torch.float32, device=dev)
+        self.flags = torch.zeros(2 * 8, dtype=torch.int32, device=dev)
+        self.words = torch.zeros(2, dtype=torch.int32, device=dev)          # call count, block counter
+        self.offsets, off = [], 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + k].view(p.shape)
+                st = self.state[p]
+                st['step'] = torch.tensor(0.0)
+                st['exp_avg'] = self.flat_m[off:off + k].view(p.shape)
+                st['exp_avg_sq'] = self.flat_v[off:off + k].view(p.shape)
+                self.offsets.append(off)
+                off += k
+        F.grad_bucket = self.flat_g
+        if self.world > 1:
+            self.peer_p = open_peers(self.flat_p, group)
+            self.peer_g = open_peers(self.flat_g, group)
+            self.peer_f = open_peers(self.flags, group)
+            dist.barrier(group)
+        else:
+            self.peer_p, self.peer_g, self.peer_f = ([self.flat_p.data_ptr()], [self.flat_g.data_ptr()],
+                                                     [self.flags.data_ptr()])
+        self.step_dev = None
+        self.lr_scale_dev = None
+        self._t = 0
+
+    def use_device_step(self, counter):
+        self.step_dev = counter
+
+    def _comm(self):
+        c = L.PeerComm()
+        c.world, c.rank = self.world, self.rank
+        for k in range(self.world):
+            c.grads[k], c.params[k], c.flags[k] = self.peer_g[k], self.peer_p[k], self.peer_f[k]
+        c.epoch, c.done_blocks = self.words[0:1].data_ptr(), self.words[1:2].data_ptr()
+        return c
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self._t += 1
+        group = self.param_groups[0]
+        # gradients that did not land in the bucket (layer-level API, foreign autograd paths) are copied into it
+        for p, off in zip(group['params'], self.offsets):
+            g = p.grad
+            if g is None:
+                self.flat_g[off:off + p.numel()].zero_()
+            elif not (g.is_contiguous() and g.data_ptr() == self.flat_g.data_ptr() + 4 * off):
+                self.flat_g[off:off + p.numel()].copy_(g.reshape(-1))
+        b1, b2 = group['betas']
+        comm = self._comm()
+        L.check(L.lib().bbb_adam_step_peer(C.byref(comm), L.ptr(self.flat_m), L.ptr(self.flat_v), self.n,
+                                           float(group['lr']), float(b1), float(b2), float(group['eps']), self._t,
+                                           L.ptr(self.step_dev), L.ptr(self.lr_scale_dev), L.stream()),
+                'bbb_adam_step_peer')
+        return loss

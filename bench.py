@@ -51,6 +51,9 @@ def parse():
     ap.add_argument('--tf32', type=int, default=-1, help='1: tcgen05 kind::tf32 path, 0: exact fp32 FMA, -1: default')
     ap.add_argument('--eager', action='store_true', help='time the eager call sequence instead of the captured graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--comm', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: peer = gradient reduce-scatter + Adam + parameter all-gather in one kernel over NVLink '
+                         'peer memory (PeerShardedAdam); nccl = per-layer NCCL all-reduce overlapped with the backward + FusedAdam')
     ap.add_argument('--cpu-budget-s', type=float, default=25.0)
     return ap.parse_args()
 
@@ -317,7 +320,9 @@ def run_b200(args):
     torch.manual_seed(0)
     net = bnn_b200.BayesianNetwork(mp).to(dev)
     net.train()
-    opt = bnn_b200.FusedAdam(net.parameters(), lr=w['lr'])
+    peer = world > 1 and args.comm == 'peer'
+    opt = (bnn_b200.PeerShardedAdam if peer else bnn_b200.FusedAdam)(net.parameters(), lr=w['lr'])
+    diag_opt = bnn_b200.FusedAdam(net.parameters(), lr=w['lr']) if peer else opt   # rank 0's solo diagnostic pass
     bnn_b200.manual_seed(2)
     bnn_b200.set_sample_base(rank * S)          # disjoint Philox sample indices per rank
     x_h, y_h = make_inputs(w, torch)
@@ -331,7 +336,7 @@ def run_b200(args):
 
     def step(x, y, collective=True):
         net.zero_grad()
-        if world > 1 and collective:
+        if world > 1 and collective and not peer:
             with ar:                                  # per-layer all-reduce overlapped with the backward
                 loss = elbo(x, y, beta, S, sigma=sigma)[0]
                 loss.backward()
@@ -339,7 +344,7 @@ def run_b200(args):
         else:
             loss = elbo(x, y, beta, S, sigma=sigma)[0]
             loss.backward()
-        opt.step()
+        (opt if collective else diag_opt).step()      # (the peer optimiser's step is itself the collective)
         return loss
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -512,9 +517,12 @@ def run_b200(args):
                 config=dict(workload=workload_name(args.workload, w, S),
                             optimizer=('Adam applied in the backward kernels\' gradient epilogue (bbb_linear_bwd_adam; same update rule as torch.optim.Adam)'
                                        if getattr(graphed, 'optimizer_fused', False) else
-                                       'Adam, one fused multi-tensor launch (bnn_b200.FusedAdam, same update rule as torch.optim.Adam)'),
+                                       ('Adam sharded over the ranks inside the peer-memory exchange kernel (bnn_b200.PeerShardedAdam, same update rule as torch.optim.Adam)'
+                                        if peer else
+                                        'Adam, one fused multi-tensor launch (bnn_b200.FusedAdam, same update rule as torch.optim.Adam)')),
                             parallelism=f'MC samples sharded over {world} GPU(s), disjoint Philox sample indices'
-                                        + (', per-layer NCCL all-reduce of the mu/rho gradients overlapped with the backward' if world > 1 else ''),
+                                        + ((', gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory (bbb_adam_step_peer)'
+                                            if peer else ', per-layer NCCL all-reduce of the mu/rho gradients overlapped with the backward') if world > 1 else ''),
                             l2='flushed between timed steps (256 MiB write), flush outside the CUDA-event brackets',
                             step=graph_note, launches_per_step=launches_per_step,
                             eager_api_ms_per_step=eager_ms,

@@ -219,6 +219,35 @@ int bbb_adam_step(int32_t n_tensors, float *const *params, const float *const *g
                   float *const *exp_avg_sq, const int64_t *sizes, double lr, double beta1, double beta2, double eps,
                   uint32_t step, const uint32_t *step_dev, const float *lr_scale_dev, void *stream);
 
+/* ---- multi-GPU optimiser step over NVLink peer memory (the gradient exchange) -----------------------
+ * Gradient reduce-scatter + Adam + parameter all-gather in ONE kernel: rank r sums the W ranks' flat gradient
+ * buckets over its slice [r n/W, (r+1) n/W) with peer loads, applies torch.optim.Adam's update with its local
+ * exp_avg / exp_avg_sq (only that slice is ever touched), and stores the new parameters into every rank's flat
+ * parameter buffer with peer stores.  Replaces ncclAllReduce + optimiser.step() of a data-parallel step.  The
+ * gradient is the MEAN over the ranks (each rank holds the gradient of its own Monte-Carlo samples).
+ *   grads / params / flags   pointers to every rank's buffers AS MAPPED IN THIS PROCESS (cudaIpcOpenMemHandle, or the
+ *                            same process for several devices); flags: 2*world zero-initialised uint32 per rank
+ *   epoch, done_blocks       two zero-initialised device words of THIS rank (call count, block counter)
+ * Every rank must make the call once per step, on any stream; the kernel completes only when all ranks have
+ * finished with this rank's buffers.  world == 1 degenerates to a flat single-tensor Adam. */
+#define BBB_MAX_PEERS 8
+typedef struct bbb_peer_comm {
+  int32_t world, rank;
+  const float *grads[BBB_MAX_PEERS];
+  float *params[BBB_MAX_PEERS];
+  uint32_t *flags[BBB_MAX_PEERS];
+  uint32_t *epoch;
+  uint32_t *done_blocks;
+} bbb_peer_comm;
+/* let kernels of the CURRENT device load / store memory of `peer_device` (cudaDeviceEnablePeerAccess; idempotent) */
+int bbb_enable_peer_access(int32_t peer_device);
+/* map an allocation another process of this node exported with cudaIpcGetMemHandle (64-byte handle, HOST pointer)
+ * into this process for the CURRENT device; *out_ptr = mapped base + offset_bytes.  Open a handle once per process. */
+int bbb_ipc_open(const void *handle, int64_t offset_bytes, void **out_ptr);
+int bbb_adam_step_peer(const bbb_peer_comm *comm, float *exp_avg, float *exp_avg_sq, int64_t n, double lr,
+                       double beta1, double beta2, double eps, uint32_t step, const uint32_t *step_dev,
+                       const float *lr_scale_dev, void *stream);
+
 /* *counter += inc  (advances a bbb_rng.step_dev between steps; one tiny launch, graph-capturable) */
 int bbb_counter_add(uint32_t *counter, uint32_t inc, void *stream);
 

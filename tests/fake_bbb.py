@@ -312,6 +312,25 @@ class FakeLib:
             p[...] = p - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + eps)
         return 0
 
+    def bbb_enable_peer_access(self, dev):
+        return 0
+
+    def bbb_ipc_open(self, handle, off, out):
+        raise AssertionError('fake lib: no CUDA IPC')
+
+    def bbb_adam_step_peer(self, comm, exp_avg, exp_avg_sq, n, lr, b1, b2, eps, step, step_dev, lr_scale_dev, st):
+        c = comm._obj
+        assert c.world == 1 and c.rank == 0, 'fake lib: one rank only (peer memory needs GPUs)'
+        t = step + (int(_arr(step_dev, C.c_uint32, 1)[0]) if step_dev else 0)
+        if lr_scale_dev:
+            lr = lr * float(_f(lr_scale_dev, 1)[0])
+        bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+        p, g, m, v = _f(c.params[0], n), _f(c.grads[0], n), _f(exp_avg, n), _f(exp_avg_sq, n)
+        m[...] = b1 * m + (1 - b1) * g
+        v[...] = b2 * v + (1 - b2) * g * g
+        p[...] = p - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + eps)
+        return 0
+
     def bbb_counter_add(self, counter, inc, st):
         _arr(counter, C.c_uint32, 1)[0] += inc
         return 0

@@ -119,3 +119,70 @@ def test_fused_optimizer_matches_separate_adam_on_gpu():
         floor = mismatch(a, a2, 2e-2, 1e-10)
         got = mismatch(a, b, 2e-2, 1e-10)                          # v = (1-b2) g^2: the gradients agree
         assert got <= max(0.05, 3 * floor + 0.01), (got, floor)    # (up to the TF32 path's reorder noise)
+
+
+def test_peer_adam_kernel_two_ranks_on_one_device():
+    """bbb_adam_step_peer with two 'ranks' whose buffers live on this one GPU, launched on two streams: the flag
+    barriers in (peer) memory let them meet, each reduces its slice of BOTH gradient buckets, updates with its own
+    m / v and writes the new parameters into both parameter buffers.  Result == Adam on the mean gradient."""
+    import ctypes as C
+    L = bnn_b200._lib
+    lib = L.lib()
+    torch.manual_seed(0)
+    n, W = 100003, 2                                   # n % 4 != 0: the tail belongs to the last rank
+    npad = (n + 3) // 4 * 4
+    p0 = torch.randn(npad, device=DEV)
+    ps = [p0.clone(), p0.clone()]
+    gs = [torch.randn(npad, device=DEV), torch.randn(npad, device=DEV)]
+    ms = [torch.zeros(npad, device=DEV) for _ in range(W)]
+    vs = [torch.zeros(npad, device=DEV) for _ in range(W)]
+    flags = [torch.zeros(16, dtype=torch.int32, device=DEV) for _ in range(W)]
+    words = [torch.zeros(2, dtype=torch.int32, device=DEV) for _ in range(W)]
+    ref_p = torch.nn.Parameter(p0[:n].clone())
+    ref = torch.optim.Adam([ref_p], lr=1e-2)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for step in (1, 2, 3):
+        for g in gs:
+            g.normal_()
+        torch.cuda.synchronize()
+        for r in range(W):
+            comm = L.PeerComm()
+            comm.world, comm.rank = W, r
+            for k in range(W):
+                comm.grads[k], comm.params[k], comm.flags[k] = gs[k].data_ptr(), ps[k].data_ptr(), flags[k].data_ptr()
+            comm.epoch, comm.done_blocks = words[r][0:1].data_ptr(), words[r][1:2].data_ptr()
+            with torch.cuda.stream(streams[r]):
+                L.check(lib.bbb_adam_step_peer(C.byref(comm), ms[r].data_ptr(), vs[r].data_ptr(), n, 1e-2, 0.9, 0.999,
+                                               1e-8, step, None, None, streams[r].cuda_stream), 'bbb_adam_step_peer')
+        torch.cuda.synchronize()
+        ref_p.grad = (0.5 * (gs[0] + gs[1]))[:n].clone()
+        ref.step()
+        assert int(words[0][0]) == step and int(words[1][0]) == step and int(words[0][1]) == 0
+    assert torch.equal(ps[0][:n], ps[1][:n])                                  # both ranks hold the same parameters
+    assert torch.allclose(ps[0][:n], ref_p.detach(), rtol=2e-6, atol=1e-7), float((ps[0][:n] - ref_p).abs().max())
+    half = (n // 4) // 2 * 4
+    assert float(ms[0][half:].abs().max()) == 0.0 and float(ms[1][:half].abs().max()) == 0.0   # state is sharded
+
+
+def test_peer_sharded_adam_single_gpu_equals_fused_adam():
+    """One rank: PeerShardedAdam (flat re-homed parameters, bucket gradients) == FusedAdam on the same Philox steps."""
+    from bnn_b200 import functional as F
+    c = Case('cfg4_bandit')
+    x, y = c.x.to(DEV), torch.randn(c.B, 1, device=DEV)
+    res = []
+    try:
+        for peer in (False, True):
+            F.grad_bucket = None
+            net = PC.build_net(c, DEV).train()
+            opt = (bnn_b200.PeerShardedAdam if peer else bnn_b200.FusedAdam)(net.parameters(), lr=1e-3)
+            bnn_b200.manual_seed(3, 0)
+            for _ in range(3):
+                net.zero_grad()
+                net.sample_elbo(x, y, c.beta, c.S)[0].backward()
+                opt.step()
+            res.append([p.detach().clone() for p in net.parameters()])
+    finally:
+        F.grad_bucket = None
+    for a, b in zip(*res):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), float((a - b).abs().max())

@@ -114,6 +114,34 @@ def test_fused_adam_matches_torch_adam(fake):
         assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
 
 
+def test_peer_sharded_adam_single_rank_is_adam(fake):
+    """PeerShardedAdam with one rank: parameters re-homed into one flat buffer (same values, views), gradients land in
+    the flat bucket the network-level backward writes, the update equals torch.optim.Adam, state names are torch's."""
+    from bnn_b200 import functional as F
+    c = Case('small_cls_mix')
+    ref_net = PC.build_net(c, 'cpu').train()
+    net = PC.build_net(c, 'cpu').train()
+    ref = torch.optim.Adam(ref_net.parameters(), lr=3e-3)
+    try:
+        opt = bnn_b200.PeerShardedAdam(net.parameters(), lr=3e-3)
+        assert opt.world == 1 and opt.reduces_gradients
+        for p, q in zip(ref_net.parameters(), net.parameters()):
+            assert torch.equal(p, q) and q.data_ptr() >= opt.flat_p.data_ptr()
+        with bnn_b200.eps_mode('reference'):
+            for it in range(3):
+                for n_, o_ in ((ref_net, ref), (net, opt)):
+                    torch.manual_seed(5 + it)
+                    n_.zero_grad()
+                    n_.sample_elbo(c.x, c.y, c.beta, c.S)[0].backward()
+                    o_.step()
+                assert net.l1.weight_mu.grad.data_ptr() == opt.flat_g.data_ptr()      # the bucket, not a copy
+        for p, q in zip(ref_net.parameters(), net.parameters()):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), float((p - q).abs().max())
+            assert torch.allclose(ref.state[p]['exp_avg_sq'], opt.state[q]['exp_avg_sq'], rtol=1e-5, atol=1e-12)
+    finally:
+        F.grad_bucket = None
+
+
 def test_beta_may_be_a_tensor(fake):
     c = Case('small_cls_mix')
     outs = []

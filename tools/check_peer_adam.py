@@ -1,0 +1,61 @@
+"""2+ GPU check (torchrun): PeerShardedAdam (reduce-scatter + Adam + all-gather in one kernel over NVLink peer
+memory) == NCCL all-reduce of the gradients + FusedAdam, same Philox draws, a few steps; then the graphed step."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bnn_b200  # noqa: E402
+from bnn_b200 import functional as F, parallel  # noqa: E402
+
+
+def build(dev):
+    torch.manual_seed(0)
+    mp = dict(input_shape=784, classes=10, batch_size=128, hidden_units=1200, mode='classification',
+              mu_init=[-0.2, 0.2], rho_init=[-5, -4], prior_init=[0.5, 0, -8], mixture_prior=True, tf32=False)
+    return bnn_b200.BayesianNetwork(mp).to(dev).train()
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(128, 784, generator=g).to(dev)
+    y = torch.randint(0, 10, (128,), generator=g).to(dev)
+    S = 2
+    res = []
+    for peer in (False, True):
+        F.grad_bucket = None
+        net = build(dev)
+        opt = (bnn_b200.PeerShardedAdam if peer else bnn_b200.FusedAdam)(net.parameters(), lr=1e-3)
+        bnn_b200.manual_seed(7, 0)
+        bnn_b200.set_sample_base(rank * S)
+        for _ in range(4):
+            net.zero_grad()
+            net.sample_elbo(x, y, 0.5, S)[0].backward()
+            if not peer:
+                parallel.allreduce_gradients(net, world)
+            opt.step()
+        torch.cuda.synchronize()
+        res.append([p.detach().clone() for p in net.parameters()])
+    worst = 0.0
+    for a, b in zip(*res):
+        bad = float((~torch.isclose(a, b, rtol=1e-4, atol=2e-6)).float().mean())
+        worst = max(worst, bad)
+    # every rank must hold identical parameters after the peer steps
+    flat = torch.cat([p.reshape(-1) for p in res[1]])
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    same = bool(torch.equal(flat, ref))
+    print(f'rank {rank}: mismatching fraction vs all-reduce + FusedAdam {worst:.2e}; identical across ranks: {same}', flush=True)
+    assert worst < 1e-3 and same
+    dist.barrier()
+    os._exit(0)
+
+
+if __name__ == '__main__':
+    main()

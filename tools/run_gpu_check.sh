@@ -1,8 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_gpu_tf32.py tests/test_gpu_head.py -q -m gpu 2>&1 | tail -2
-timeout 180 python bench.py --workload wide --samples 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_big5.json 2> gpurun_out/bench_big5.err; echo "bench rc=$?"
-python -c "
-import json; d=json.loads(open('gpurun_out/bench_big5.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['step_roofline']['achieved_tflops'], d['roofline']['frac'], d['e2e'])"
-timeout 300 python bench.py --workload wide --samples 8 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_big6.json 2> gpurun_out/bench_big6.err; echo "bench rc=$?"
-python -c "
-import json; d=json.loads(open('gpurun_out/bench_big6.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['step_roofline']['achieved_tflops'], d['roofline']['frac'], d['e2e'])"
+for comm in nccl peer nccl peer; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 100 --warmup 5 --comm $comm > gpurun_out/bench_n2_$comm.json 2> gpurun_out/bench_n2_$comm.err; echo "rc=$?"
+tail -1 gpurun_out/bench_n2_$comm.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$comm', d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'], d['config']['launches_per_step'])"
+done
+timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('single', d['ms_per_step'], d['value'])"
