@@ -42,17 +42,19 @@ def _f32c(t):
 grad_ready_hook = None
 
 
-# A persistent flat gradient bucket (optim.PeerShardedAdam installs one that the other ranks can read over NVLink):
-# when set and large enough, the network-level backward writes its gradients there instead of a fresh allocation.
-grad_bucket = None
+# Persistent flat gradient buckets, keyed by the address of the flat parameter buffer they belong to
+# (optim.PeerShardedAdam registers one that the other ranks can read over NVLink): the network-level backward of a
+# network whose parameters live in that buffer writes its gradients there instead of into a fresh allocation.
+grad_buckets = {}
 
 
 def _alloc_grads(params):
     """Gradient buffers for every layer as consecutive views of ONE flat tensor, in parameter order, so a
     multi-GPU step can all-reduce them with a single collective and no copies (parallel.py)."""
     total = sum(t.numel() for p in params for t in p)
-    if grad_bucket is not None and grad_bucket.numel() >= total and grad_bucket.device == params[0][0].device:
-        flat = grad_bucket[:total]
+    bucket = grad_buckets.get(params[0][0].data_ptr())
+    if bucket is not None and bucket.numel() >= total and bucket.device == params[0][0].device:
+        flat = bucket[:total]
     else:
         flat = torch.empty(total, dtype=torch.float32, device=params[0][0].device)
     out, off = [], 0
@@ -406,6 +408,7 @@ class _FusedELBO(torch.autograd.Function):
             ctx.dxs = dxs
         ctx.cfg = (prior, S, beta_h, tf32, eps, len(params))
         ctx.beta_dev = beta_d
+        ctx.set_materialize_grads(False)      # no zero-filled gradients for the three non-differentiable scalars
         ctx.fused_opt, ctx.live = fused_opt if fused_opt is not None else (None, None)
         loss, lp, lq, nl = out4[0:1], out4[1], out4[2], out4[3:4]
         ctx.mark_non_differentiable(lp, lq, nl)
@@ -414,6 +417,8 @@ class _FusedELBO(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, *unused):
         prior, S, beta, tf32, eps, nl = ctx.cfg
+        if g_loss is None:
+            return (None,) * (9 + 4 * nl)
         sv = ctx.saved_tensors
         x2, d_out = sv[0], sv[1]
         params = [tuple(_f32c(t) for t in sv[2 + 4 * i:6 + 4 * i]) for i in range(nl)]
@@ -638,6 +643,7 @@ class _FusedELBOLR(torch.autograd.Function):
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *deltas, *eps.tensors())
         ctx.cfg = (sigma_p, S, beta_h, eps, len(params))
         ctx.tf32 = tf32
+        ctx.set_materialize_grads(False)
         ctx.beta_dev = beta_d
         loss, klm, nl = out4[0:1], out4[1], out4[2:3]
         ctx.mark_non_differentiable(klm, nl)
@@ -646,6 +652,8 @@ class _FusedELBOLR(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, *unused):
         sigma_p, S, beta, eps, nl = ctx.cfg
+        if g_loss is None:
+            return (None,) * (8 + 4 * nl)
         sv = ctx.saved_tensors
         x2, d_out = sv[0], sv[1]
         params = [tuple(_f32c(t) for t in sv[2 + 4 * i:6 + 4 * i]) for i in range(nl)]

@@ -117,7 +117,7 @@ class PeerShardedAdam(torch.optim.Optimizer):
     over the gradients, and each rank touches 1/world of the optimiser state.
 
     The parameters are re-homed into one flat buffer (their `.data` become views of it, same values, same
-    layout) and the network-level backward writes its gradients into one flat bucket (functional.grad_bucket);
+    layout) and the network-level backward writes its gradients into one flat bucket (functional.grad_buckets);
     both are opened by every rank of the node through CUDA IPC.  Every rank must call step() once per step.
     Same update rule and state names as torch.optim.Adam (the per-parameter `exp_avg` / `exp_avg_sq` are views of the
     flat state; only this rank's slice of them is ever non-zero)."""
@@ -160,7 +160,7 @@ class PeerShardedAdam(torch.optim.Optimizer):
                 st['exp_avg_sq'] = self.flat_v[off:off + k].view(p.shape)
                 self.offsets.append(off)
                 off += k
-        F.grad_bucket = self.flat_g
+        F.grad_buckets[self.flat_p.data_ptr()] = self.flat_g    # this network's backward writes its gradients here
         if self.world > 1:
             self.peer_p = open_peers(self.flat_p, group)
             self.peer_g = open_peers(self.flat_g, group)

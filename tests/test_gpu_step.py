@@ -173,7 +173,7 @@ def test_peer_sharded_adam_single_gpu_equals_fused_adam():
     res = []
     try:
         for peer in (False, True):
-            F.grad_bucket = None
+            F.grad_buckets.clear()
             net = PC.build_net(c, DEV).train()
             opt = (bnn_b200.PeerShardedAdam if peer else bnn_b200.FusedAdam)(net.parameters(), lr=1e-3)
             bnn_b200.manual_seed(3, 0)
@@ -183,6 +183,6 @@ def test_peer_sharded_adam_single_gpu_equals_fused_adam():
                 opt.step()
             res.append([p.detach().clone() for p in net.parameters()])
     finally:
-        F.grad_bucket = None
+        F.grad_buckets.clear()
     for a, b in zip(*res):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), float((a - b).abs().max())

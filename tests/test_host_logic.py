@@ -139,7 +139,7 @@ def test_peer_sharded_adam_single_rank_is_adam(fake):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), float((p - q).abs().max())
             assert torch.allclose(ref.state[p]['exp_avg_sq'], opt.state[q]['exp_avg_sq'], rtol=1e-5, atol=1e-12)
     finally:
-        F.grad_bucket = None
+        F.grad_buckets.clear()
 
 
 def test_beta_may_be_a_tensor(fake):

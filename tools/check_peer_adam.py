@@ -29,7 +29,7 @@ def main():
     S = 2
     res = []
     for peer in (False, True):
-        F.grad_bucket = None
+        F.grad_buckets.clear()
         net = build(dev)
         opt = (bnn_b200.PeerShardedAdam if peer else bnn_b200.FusedAdam)(net.parameters(), lr=1e-3)
         bnn_b200.manual_seed(7, 0)
