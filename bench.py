@@ -314,7 +314,9 @@ def run_b200(args):
     w = dict(WORKLOADS[args.workload])
     S = args.samples or w['S']                 # per-GPU MC samples (weak scaling over the sample axis)
     # default: the tcgen05 kind::tf32 path where the layers are wide enough to be dense contractions
-    tf32 = (args.tf32 == 1) or (args.tf32 < 0 and args.workload in ('mnist', 'mnist_lr', 'wide'))
+    # (measured: regression 0.211 vs 0.332 ms, bandit 0.141 vs 0.172 ms; layers whose rows are not 16-byte multiples
+    # -- in = 1, in = 119 -- and the heads run the exact fp32 kernels in either mode)
+    tf32 = (args.tf32 == 1) or (args.tf32 < 0)
     mp = model_params(w)
     mp['tf32'] = tf32
     torch.manual_seed(0)
@@ -510,6 +512,35 @@ def run_b200(args):
             cpu = json.loads(out.stdout.strip().splitlines()[-1])['cpu_baseline']
         except Exception as e:     # the baseline is reported, never required for the GPU number
             cpu = dict(value=None, unit='batch*MC samples/s', cores=None, kind='port', sample=f'failed: {e}')
+    action = None
+    if args.workload == 'bandit' and world == 1:
+        # latency of Bandit.take_action's scoring (base_bandit.py:43-46): 2 actions x n_samples = 2
+        # forwards of batch 1 in eval mode, then the host reads the two scores.  (i) as the reference does it --
+        # net(x) with sample=False, i.e. mean weights; (ii) with posterior sampling, one batched
+        # launch per layer (net.sample_predict on the two candidate rows).  Wall clock including the host read.
+        net.eval()
+        rows = x_d[:2].contiguous()
+
+        def score_mean():
+            with torch.no_grad():
+                r = [sum(net(rows[i:i + 1]) for _ in range(2)) for i in range(2)]
+            return float(r[0]), float(r[1])
+
+        def score_sampled():
+            with torch.no_grad():
+                o = net.sample_predict(rows, 2).sum(0)
+            return o.cpu().tolist()
+
+        action = {}
+        for tag, fn in (('mean_weights_reference_semantics', score_mean), ('posterior_sampled_batched', score_sampled)):
+            for _ in range(10):
+                fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(100):
+                fn()
+            action[tag + '_us'] = (time.perf_counter() - t0) / 100 * 1e6
+        net.train()
     line = dict(metric='bbb_elbo_train_throughput', value=value, unit='batch*MC samples/s', n_gpus=world,
                 steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, steps_per_s=1e3 / ms,
                 higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -533,6 +564,8 @@ def run_b200(args):
                          d2h_bytes_per_step=4),
                 gpu_launches=int(launches), clocks=clk, roofline=roof, step_roofline=step_roof,
                 kernels=kern_table, cpu_baseline=cpu)
+    if action is not None:
+        line['action_scoring'] = action
     print(json.dumps(line), flush=True)
     if world > 1:
         finish(dist, torch)
