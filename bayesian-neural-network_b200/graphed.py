@@ -24,6 +24,9 @@ class GraphedTrainStep:
         dev = x.device
         self.beta = torch.full((1,), float(beta), dtype=torch.float32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)      # read as uint32 by the kernels
+        # d loss / d loss, allocated once: loss.backward() would launch a ones_like fill between the head's forward
+        # and backward kernels in every step, which also breaks their programmatic-dependent-launch chain
+        self._one = torch.ones(1, dtype=torch.float32, device=dev)
         self._elbo = net.sample_elbo_lr if net.local_reparam else net.sample_elbo
         # an optimiser that exchanges the gradients itself (PeerShardedAdam) needs no all-reduce around the backward
         self._ar = parallel.OverlappedAllReduce(1 if getattr(optimizer, 'reduces_gradients', False) else world_size)
@@ -70,7 +73,7 @@ class GraphedTrainStep:
         self.net.zero_grad(set_to_none=True)
         with self._ar:
             info = self._elbo(self.x, self.y, self.beta, self.samples, sigma=self.sigma)
-            info[0].backward()
+            info[0].backward(self._one)
         self._ar.join(self.net)
         self.opt.step()
         L.check(L.lib().bbb_counter_add(self.counter.data_ptr(), 1, L.stream()), 'bbb_counter_add')
