@@ -176,6 +176,12 @@ class PeerShardedAdam(torch.optim.Optimizer):
     def use_device_step(self, counter):
         self.step_dev = counter
 
+    def release(self):
+        """Stop routing this network's gradients into the shared bucket (the mapped peer memory itself stays mapped
+        for the life of the process: the other ranks may still hold it)."""
+        from . import functional as F
+        F.grad_buckets.pop(self.flat_p.data_ptr(), None)
+
     def _comm(self):
         c = L.PeerComm()
         c.world, c.rank = self.world, self.rank

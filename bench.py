@@ -323,7 +323,22 @@ def run_b200(args):
     net = bnn_b200.BayesianNetwork(mp).to(dev)
     net.train()
     peer = world > 1 and args.comm == 'peer'
-    opt = (bnn_b200.PeerShardedAdam if peer else bnn_b200.FusedAdam)(net.parameters(), lr=w['lr'])
+    peer_note = ''
+    opt = None
+    if peer:
+        # every rank must take the same path: agree on whether the peer mapping (CUDA IPC + NVLink peer access) came up
+        try:
+            opt = bnn_b200.PeerShardedAdam(net.parameters(), lr=w['lr'])
+            ok = 1
+        except Exception as e:                          # e.g. an allocator configuration whose blocks cannot be exported
+            ok, peer_note = 0, f' (peer mapping unavailable: {type(e).__name__}: {e}; NCCL all-reduce path used)'
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0:
+            peer, opt = False, None
+            peer_note = peer_note or ' (peer mapping unavailable on another rank; NCCL all-reduce path used)'
+    if opt is None:
+        opt = bnn_b200.FusedAdam(net.parameters(), lr=w['lr'])
     diag_opt = bnn_b200.FusedAdam(net.parameters(), lr=w['lr']) if peer else opt   # rank 0's solo diagnostic pass
     bnn_b200.manual_seed(2)
     bnn_b200.set_sample_base(rank * S)          # disjoint Philox sample indices per rank
@@ -553,7 +568,7 @@ def run_b200(args):
                                         'Adam, one fused multi-tensor launch (bnn_b200.FusedAdam, same update rule as torch.optim.Adam)')),
                             parallelism=f'MC samples sharded over {world} GPU(s), disjoint Philox sample indices'
                                         + ((', gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory (bbb_adam_step_peer)'
-                                            if peer else ', per-layer NCCL all-reduce of the mu/rho gradients overlapped with the backward') if world > 1 else ''),
+                                            if peer else ', per-layer NCCL all-reduce of the mu/rho gradients overlapped with the backward' + peer_note) if world > 1 else ''),
                             l2='flushed between timed steps (256 MiB write), flush outside the CUDA-event brackets',
                             step=graph_note, launches_per_step=launches_per_step,
                             eager_api_ms_per_step=eager_ms,
