@@ -195,6 +195,7 @@ extern "C" int bbb_lr_linear_bwd(const float *dy, const float *dy_mask_src, cons
   a.vec_in = (in % 4 == 0) && all16({x});
   a.vec_out = (out % 4 == 0) && all16({w_mu, w_rho, eps_a, dy, dy_mask_src, delta});
   if ((flags & BBB_F_TF32) && lr_bwd_tc_supported(a)) return launch_lr_bwd_tc(a, (cudaStream_t)stream);
+  if (a.S > 0 && a.B > 0 && lr_head_bwd_supported(a)) return launch_lr_bwd_head(a, (cudaStream_t)stream);   // out <= 16
   if (a.S > 0 && a.B > 0 && lr_narrow_supported(a)) return launch_lr_bwd_narrow(a, (cudaStream_t)stream);
   return launch_lr_bwd_fma(a, (cudaStream_t)stream);
 }

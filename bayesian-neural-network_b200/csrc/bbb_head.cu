@@ -549,6 +549,223 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const LinArgs a_in, int cw
   }
 }
 
+// ==================================================================================================
+// local-reparameterisation head backward (weights [in, out], out <= 16; networks.py:116-138 differentiated):
+//   dV = dz eps_a / (2 delta);   g1[i][o] = sum_{s,b} x dz;   g2[i][o] = sum_{s,b} x^2 dV
+//   grad_mu = g1 + gk mu / sp^2;   grad_rho = sigmoid(rho) (2 sigma g2 + gk (sigma / sp^2 - 1 / sigma))
+//   dx[b][i] = sum_o dz mu[i][o] + 2 x sum_o dV sigma^2[i][o]
+// Same organisation as head_bwd_kernel: a CTA owns the weight rows i_lo .. i_lo + cw completely, a pass covers up to
+// 256 (sample, batch-row) pairs, one per thread, with its dz / dV rows and x columns in registers.  mu and sigma are
+// sample-independent, so g1 / g2 simply accumulate over every pass in the registers of their (i, o) item threads; no
+// weight is sampled here -- only the activation noise eps_a is regenerated, one Philox call per quad of the
+// pair's output row.
+// ==================================================================================================
+template <int NOUT, bool EXACT>
+__global__ void __launch_bounds__(HT) lr_head_bwd_kernel(const LrArgs a_in, int cw, int spp, int rbp) {
+  extern __shared__ __align__(16) float dynb[];          // dz_s [pair][DZP] | dv_s [pair][DZP] | x_s [pair][XP]
+  __shared__ float Mu[CWM][NO], S2[CWM][NO];             // this CTA's rows of mu and sigma^2
+  __shared__ float Gp[2][NG][CWM * NO];                  // per batch group partial g1 / g2 of a pass
+  __shared__ float Cp[SPM][NO];                          // per sample of the pass: sum_b dz  (bias gradients)
+  pdl_launch_dependents();
+  pdl_wait();
+  LrArgs a = a_in;
+  head_rng_resolve(a.rng);
+  float *dz_s = dynb, *dv_s = dynb + RP * DZP, *x_s = dynb + 2 * RP * DZP;
+  const int tid = threadIdx.x;
+  const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN, wgrad = !(a.flags & BBB_F_NO_WGRAD);
+  const bool want_dx = !(a.flags & BBB_F_NO_DX), dx_preact = a.flags & BBB_F_DX_PREACT, accum = a.flags & BBB_F_ACCUM;
+  const int out = EXACT ? NOUT : (int)a.out;
+  auto col_ok = [&](int o) { return EXACT || o < out; };
+  const int64_t i_lo = (int64_t)blockIdx.x * cw;
+  const int w = (int)min((int64_t)cw, a.in - i_lo), nqc = w >> 2;
+  const bool bias_cta = blockIdx.x == 0;
+  const float osc = a.out_scale_dev ? __ldg(a.out_scale_dev) : 1.0f;
+  const float dxs = ((a.flags & BBB_F_SCALE_DX) && a.out_scale_dev) ? osc : 1.0f;
+  const float gk = (a.flags & BBB_F_LOGPROB) ? a.g_kl * (a.g_kl_dev ? __ldg(a.g_kl_dev) : 1.0f) : 0.0f;
+  const float inv_sp2 = 1.0f / (a.sigma_p * a.sigma_p);
+
+  // item thread t < w * out owns weight (i_lo + t / out, t % out): mu, sigma once; g1, g2 over all passes
+  const bool ithread = tid < w * out;
+  const int wi = ithread ? tid / out : 0, wo = ithread ? tid - wi * out : 0;
+  const int64_t we = (i_lo + wi) * a.out + wo;
+  float mu = 0.0f, sg = 1.0f, g1 = 0.0f, g2 = 0.0f, gbmu = 0.0f, gbrho = 0.0f;
+  if (ithread) {
+    mu = __ldcg(a.w_mu + we);
+    sg = softplus_f(__ldcg(a.w_rho + we));
+    Mu[wi][wo] = mu;
+    S2[wi][wo] = sg * sg;
+  }
+  const int items = w * out;
+  const int it = tid % 64, grp = tid / 64;                // 64 item lanes x 4 batch groups; items beyond 64: second round
+
+  for (int s0 = 0; s0 < a.S; s0 += spp) {
+    const int ns = min(spp, a.S - s0);
+    if (tid < SPM * NO) Cp[tid / NO][tid % NO] = 0.0f;
+    float p1[(CWM * NO + 63) / 64], p2[(CWM * NO + 63) / 64];
+#pragma unroll
+    for (int r = 0; r < (CWM * NO + 63) / 64; ++r) p1[r] = p2[r] = 0.0f;
+    for (int64_t b0 = 0; b0 < a.B; b0 += rbp) {
+      const int nb = (int)min((int64_t)rbp, a.B - b0);
+      const int pairs = ns * nb;
+      const int p_sl = tid / nb, p_b = tid - p_sl * nb;
+      const bool p_ok = tid < pairs;
+      float4 xq[CWM / 4];
+      float dzr[NOUT], dvr[NOUT];
+      {
+        const float *xs = a.x + (int64_t)(s0 + p_sl) * a.x_sstride + (b0 + p_b) * a.in + i_lo;
+#pragma unroll
+        for (int q = 0; q < CWM / 4; ++q)
+          xq[q] = (p_ok && q < nqc) ? __ldg(reinterpret_cast<const float4 *>(xs) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int s = s0 + p_sl;
+        const int64_t row = (int64_t)(b0 + p_b) * out;                 // index of (b, o = 0) inside the sample
+        const int64_t base = (int64_t)s * a.B * a.out + row;
+        float dl[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+          float z = (p_ok && col_ok(o)) ? __ldg(a.dy + base + o) : 0.0f;
+          if (a.mask && p_ok && col_ok(o) && !(__ldg(a.mask + base + o) > 0.0f)) z = 0.0f;
+          dzr[o] = z;
+          dl[o] = (sample && p_ok && col_ok(o)) ? __ldg(a.delta_in + base + o) : 0.0f;
+          dvr[o] = 0.0f;
+        }
+        if (sample && p_ok) {
+          if (a.eps_a) {
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o)
+              if (col_ok(o) && dl[o] > 0.0f) dvr[o] = dzr[o] * __ldg(a.eps_a + base + o) / (2.0f * dl[o]);
+          } else {
+            // eps_a of elements row .. row + out - 1: the Philox quads that cover them, one call each
+            const uint32_t smp = a.rng.sample_base + (uint32_t)s;
+            int64_t q4 = row >> 2;
+            float e4[4];
+            philox_normal4(a.rng, a.rng.tensor_w, smp, (uint32_t)q4, e4);
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) {
+              if (col_ok(o)) {
+                const int64_t idx = row + o;
+                if ((idx >> 2) != q4) { q4 = idx >> 2; philox_normal4(a.rng, a.rng.tensor_w, smp, (uint32_t)q4, e4); }
+                const int l = (int)(idx & 3);
+                const float ep = l == 0 ? e4[0] : l == 1 ? e4[1] : l == 2 ? e4[2] : e4[3];
+                if (dl[o] > 0.0f) dvr[o] = dzr[o] * ep / (2.0f * dl[o]);
+              }
+            }
+          }
+        }
+      }
+      if (p_ok) {
+#pragma unroll
+        for (int q = 0; q < CWM / 4; ++q) {
+          if (relu) { xq[q].x = fmaxf(xq[q].x, 0.f); xq[q].y = fmaxf(xq[q].y, 0.f); xq[q].z = fmaxf(xq[q].z, 0.f); xq[q].w = fmaxf(xq[q].w, 0.f); }
+          if (q < nqc) *reinterpret_cast<float4 *>(x_s + tid * XP + 4 * q) = xq[q];
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) { dz_s[tid * DZP + o] = dzr[o]; dv_s[tid * DZP + o] = dvr[o]; }
+      }
+      __syncthreads();   // (B) dz_s, dv_s, x_s (and Mu / S2 on the first pass) visible
+      if (wgrad) {
+        // g1 / g2 partial sums: item = (i, o) in rounds of 64, this thread's quarter of the pairs
+        const int pA = (int)((int64_t)grp * pairs / NG), pB = (int)((int64_t)(grp + 1) * pairs / NG);
+#pragma unroll
+        for (int r = 0; r < (CWM * NO + 63) / 64; ++r) {
+          const int item = it + 64 * r;
+          if (item < items) {
+            const int i = item / out, o = item - i * out;
+            float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 4
+            for (int p = pA; p < pB; ++p) {
+              const float x = x_s[p * XP + i];
+              s1 = fmaf(x, dz_s[p * DZP + o], s1);
+              s2 = fmaf(x * x, dv_s[p * DZP + o], s2);
+            }
+            p1[r] += s1; p2[r] += s2;
+          }
+        }
+        if (bias_cta && tid < ns * out) {
+          const int sl = tid / out, o = tid - sl * out;
+          float c = 0.0f;
+          for (int b = 0; b < nb; ++b) c += dz_s[(sl * nb + b) * DZP + o];
+          Cp[sl][o] += c;
+        }
+      }
+      if (want_dx && p_ok) {       // one row of dx per thread, its columns complete
+        float *dxr = a.dx + ((int64_t)(s0 + p_sl) * a.B + b0 + p_b) * a.in + i_lo;
+#pragma unroll
+        for (int q = 0; q < CWM / 4; ++q) {
+          if (q < nqc) {
+            const float xv[4] = {xq[q].x, xq[q].y, xq[q].z, xq[q].w};
+            float d[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+              for (int o = 0; o < NOUT; ++o) {
+                if (col_ok(o)) {
+                  t1 = fmaf(dzr[o], Mu[4 * q + c][o], t1);
+                  t2 = fmaf(dvr[o], S2[4 * q + c][o], t2);
+                }
+              }
+              d[c] = dxs * fmaf(2.0f * xv[c], t2, t1);
+              if (dx_preact && !(xv[c] > 0.0f)) d[c] = 0.0f;
+            }
+            *reinterpret_cast<float4 *>(dxr + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);
+          }
+        }
+      }
+      __syncthreads();   // (C) this pass's shared tiles are consumed
+    }
+    // bias gradients of the pass's samples (CTA 0): sum_b dz, weighted by eps_b for rho
+    if (wgrad && bias_cta && tid < out) {
+      for (int sl = 0; sl < ns; ++sl) {
+        const float c = Cp[sl][tid];
+        gbmu += c;
+        if (sample) {
+          const int s = s0 + sl;
+          const float eb = a.eps_b ? __ldg(a.eps_b + (int64_t)s * a.out + tid)
+                                   : philox_normal1(a.rng, a.rng.tensor_b, a.rng.sample_base + (uint32_t)s, (uint64_t)tid);
+          gbrho += c * eb;
+        }
+      }
+    }
+    // fold the pass's partial sums of the 4 batch groups into the item threads
+    if (wgrad) {
+#pragma unroll
+      for (int r = 0; r < (CWM * NO + 63) / 64; ++r) {
+        const int item = it + 64 * r;
+        if (item < items) { Gp[0][grp][item] = p1[r]; Gp[1][grp][item] = p2[r]; }
+      }
+    }
+    __syncthreads();
+    if (wgrad && ithread) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) { g1 += Gp[0][g][tid]; g2 += Gp[1][g][tid]; }
+    }
+    __syncthreads();     // Gp / Cp are rewritten by the next pass
+  }
+  if (wgrad && ithread) {
+    const float gm = fmaf(gk * mu, inv_sp2, g1);
+    const float gr = -expm1f(-sg) * (2.0f * sg * g2 + gk * (sg * inv_sp2 - 1.0f / sg));
+    a.g_w_mu[we] = accum ? fmaf(osc, gm, a.g_w_mu[we]) : osc * gm;
+    a.g_w_rho[we] = accum ? fmaf(osc, gr, a.g_w_rho[we]) : osc * gr;
+  }
+  if (wgrad && bias_cta && tid < out) {
+    const float bmu = __ldcg(a.b_mu + tid), bsg = softplus_f(__ldcg(a.b_rho + tid));
+    const float gm = fmaf(gk * bmu, inv_sp2, gbmu);
+    const float gr = -expm1f(-bsg) * (gbrho + gk * (bsg * inv_sp2 - 1.0f / bsg));
+    a.g_b_mu[tid] = accum ? fmaf(osc, gm, a.g_b_mu[tid]) : osc * gm;
+    a.g_b_rho[tid] = accum ? fmaf(osc, gr, a.g_b_rho[tid]) : osc * gr;
+  }
+}
+
+constexpr int kLrBwdDyn = (2 * RP * DZP + RP * XP) * 4;
+
+template <int NOUT, bool EXACT>
+int launch_lr_head_bwd_t(const LrArgs &a, int grid, int cw, int spp, int rbp, cudaStream_t st) {
+  BBB_CHECK_CUDA(cudaFuncSetAttribute(lr_head_bwd_kernel<NOUT, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLrBwdDyn));
+  BBB_CHECK_CUDA(launch_pdl(lr_head_bwd_kernel<NOUT, EXACT>, dim3(grid), dim3(HT), kLrBwdDyn, st, a, cw, spp, rbp));
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
 inline int cdiv_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -673,6 +890,30 @@ int launch_linear_bwd_head(const LinArgs &a, cudaStream_t st) {
   if (wq > CWM / 4) wq = CWM / 4;
   if (wq < 1) wq = 1;
 #define CALL(N, E) return launch_head_bwd_t<N, E>(a, cdiv_i(nq_i, wq), wq * 4, spp, rbp, st)
+  BBB_HEAD_DISPATCH(a.out, CALL);
+#undef CALL
+}
+
+bool lr_head_bwd_supported(const LrArgs &a) {
+  return a.out >= 1 && a.out <= NO && a.vec_in && a.in >= 4 && a.B >= 1 && a.S >= 1 && a.S <= 65535;
+}
+
+int launch_lr_bwd_head(const LrArgs &a, cudaStream_t st) {
+  const int nq_i = (int)(a.in / 4);
+  int spp = 1, rbp = RP;
+  if (a.B <= RP / 2) {
+    spp = (int)(RP / a.B);
+    if (spp > SPM) spp = SPM;
+    if (spp > a.S) spp = a.S;
+    rbp = (int)a.B;
+  }
+  int wq = cdiv_i(nq_i, kSMs);               // about one range of weight rows per SM; w * out <= 256 item threads
+  int cap = HT / (4 * (int)a.out);
+  if (cap < 1) cap = 1;
+  if (wq > cap) wq = cap;
+  if (wq > CWM / 4) wq = CWM / 4;
+  if (wq < 1) wq = 1;
+#define CALL(N, E) return launch_lr_head_bwd_t<N, E>(a, cdiv_i(nq_i, wq), wq * 4, spp, rbp, st)
   BBB_HEAD_DISPATCH(a.out, CALL);
 #undef CALL
 }

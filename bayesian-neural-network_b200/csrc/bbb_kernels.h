@@ -98,6 +98,8 @@ int launch_lr_bwd_narrow(const LrArgs &a, cudaStream_t st);
 bool head_supported(const LinArgs &a);
 int launch_linear_fwd_head(const LinArgs &a, cudaStream_t st);
 int launch_linear_bwd_head(const LinArgs &a, cudaStream_t st);
+bool lr_head_bwd_supported(const LrArgs &a);
+int launch_lr_bwd_head(const LrArgs &a, cudaStream_t st);   // LR head backward, exact fp32, same organisation
 
 // fused backward (wgrad + analytic epilogue + dgrad, one eps regeneration) for batches of at most 128 rows
 // (bbb_linear_bwd_fused.cu)
