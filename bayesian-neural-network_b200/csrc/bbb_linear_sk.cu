@@ -116,9 +116,11 @@ __global__ void __launch_bounds__(NT2, kCtaPerSm) fwd_sk_kernel(const LinArgs a_
   __shared__ Ctl2 ctl;
   __shared__ float bias_s[SG][BN];
   __shared__ float red[64];
+  __shared__ int last_s0;
   LinArgs a = a_in;
   uint8_t *tiles = align1024(dsm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) last_s0 = -1;      // (ordered before its use by the barrier in ctl2_setup)
   const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN, x_shared = a.x_sstride == 0;
   int u0, u1;
   unit_range(total, u0, u1);
@@ -146,11 +148,36 @@ __global__ void __launch_bounds__(NT2, kCtaPerSm) fwd_sk_kernel(const LinArgs a_
   if (warp == NPW) {
     mma_warp<BN, SG>(ctl, tiles, tmem, u0, u1, nkb, o_tiles, a.S, x_shared);
   } else {
+    // A CTA's unit range may run through more than one sample group (one launch covers all groups): the registers
+    // hold the log-prob sums of group `lp_s0`; they are handed over -- warp sums, one fp64 atomic per CTA and value --
+    // when the group changes and after the last segment.
+    int lp_s0 = -1;
+    auto flush_logprob = [&]() {
+#pragma unroll
+      for (int s = 0; s < SG; ++s) {
+        const float p = warp_sum(lp[s]), q = warp_sum(lq[s]);
+        if (lane == 0) { red[s * 16 + warp] = p; red[s * 16 + 8 + warp] = q; }
+        lp[s] = lq[s] = 0.0f;
+      }
+      bar_producers();
+      if (tid < 2 * SG) {
+        const int s = tid >> 1, which = tid & 1;
+        double v = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < NPW; ++w8) v += (double)red[s * 16 + which * 8 + w8];
+        if (lp_s0 + s < a.S) atomicAdd((which ? a.logq : a.logp) + lp_s0 + s, v);
+      }
+      bar_producers();
+    };
     int it = 0, seg = 0;
     for (int u = u0; u < u1; ++seg) {
       const int tile = u / nkb, kb0 = u - tile * nkb, kb1 = min(nkb, kb0 + (u1 - u));
       const int sgi = tile / o_tiles, ot = tile - sgi * o_tiles;
       const int s0 = sgi * SG, ns = min(SG, a.S - s0);
+      if (kLogProb && s0 != lp_s0) {
+        if (lp_s0 >= 0) flush_logprob();
+        lp_s0 = s0;
+      }
       const int64_t o0 = (int64_t)ot * BN;
       const bool first = kb0 == 0;   // this segment owns the bias (value and log-prob terms)
       if (tid < BN) {
@@ -259,14 +286,15 @@ __global__ void __launch_bounds__(NT2, kCtaPerSm) fwd_sk_kernel(const LinArgs a_
       bar_producers();  // ring and bias_s are reused by the next segment
       u += kb1 - kb0;
     }
+    if (kLogProb && tid == 0) last_s0 = lp_s0;
   }
   pdl_launch_dependents();   // the main loop is done: let the next kernel of the chain become resident
   __syncthreads();
-  if (kLogProb) {  // the launcher keeps a log-prob launch inside one sample group, so lp[s] belongs to sample s
-    const int ns_all = min(SG, a.S);
+  if (kLogProb && last_s0 >= 0) {  // the last group's sums (the MMA warp holds zeros), after the dependents were let in
+    const int ns_last = min(SG, a.S - last_s0);
 #pragma unroll
     for (int s = 0; s < SG; ++s)
-      if (s < ns_all) block_sum2_atomic(lp[s], lq[s], red, a.logp + s, a.logq + s);
+      if (s < ns_last) block_sum2_atomic(lp[s], lq[s], red, a.logp + last_s0 + s, a.logq + last_s0 + s);
   }
   ctl2_teardown(ctl, R::kTmemCols);
 }
@@ -293,20 +321,10 @@ int launch_fwd(const LinArgs &a, cudaStream_t st) {
     BBB_CHECK_CUDA(cudaMemsetAsync(a.y, 0, sizeof(float) * (size_t)a.S * a.B * a.out, st));
     note_launch();
   }
-  // one launch per sample group when log-probs are accumulated (a CTA's partial sums then belong to one group)
-  const int launches = (lpq && s_groups > 1) ? s_groups : 1;
+  const int launches = 1;
   for (int l = 0; l < launches; ++l) {
     LinArgs b = a;
-    int groups = s_groups;
-    if (launches > 1) {
-      b.S = (l + 1 < launches) ? SG : a.S - l * SG;
-      b.rng.sample_base += (uint32_t)(l * SG);
-      if (b.x_sstride) b.x += (int64_t)l * SG * a.x_sstride;
-      if (b.eps_w) { b.eps_w += (int64_t)l * SG * a.out * a.in; b.eps_b += (int64_t)l * SG * a.out; }
-      b.y += (int64_t)l * SG * a.B * a.out;
-      b.logp += l * SG; b.logq += l * SG;
-      groups = 1;
-    }
+    const int groups = s_groups;
     const int total = groups * o_tiles * nkb;
     if (lpq) {
       if (int r = set_smem(fwd_sk_kernel<BN, SG, true>, smem)) return r;
