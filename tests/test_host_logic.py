@@ -215,3 +215,17 @@ def test_fuse_optimizer_refuses_what_the_kernel_cannot_do(fake):
 @pytest.mark.parametrize('name', SMALL + SMALL_LR)
 def test_batched_prediction(fake, name):
     PC.check_batched_prediction(Case(name), 'cpu')
+
+
+def test_peer_comm_struct_matches_header():
+    """ctypes mirror of struct bbb_peer_comm: array lengths follow BBB_MAX_PEERS, field order follows include/bbb.h."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, 'include', 'bbb.h')).read()
+    n = int(re.search(r'#define BBB_MAX_PEERS (\d+)', hdr).group(1))
+    L = bnn_b200._lib
+    fields = dict(L.PeerComm._fields_)
+    assert fields['grads']._length_ == n and fields['params']._length_ == n and fields['flags']._length_ == n
+    body = re.search(r'typedef struct bbb_peer_comm \{(.*?)\} bbb_peer_comm;', hdr, re.S).group(1)
+    order = re.findall(r'(world|rank|grads|params|flags|epoch|done_blocks)', body)
+    assert order == [f for f, _ in L.PeerComm._fields_]
+    assert C.sizeof(L.PeerComm) == 8 + 3 * 8 * n + 16
