@@ -45,14 +45,32 @@ grad_ready_hook = None
 # Persistent flat gradient buckets, keyed by the address of the flat parameter buffer they belong to
 # (optim.PeerShardedAdam registers one that the other ranks can read over NVLink): the network-level backward of a
 # network whose parameters live in that buffer writes its gradients there instead of into a fresh allocation.
+# Values are (flat bucket, owner): owner() (a weakref, or None) is the optimiser whose parameters the bucket serves.
 grad_buckets = {}
+
+
+def _bucket_for(params):
+    """The registered bucket of this network, or None.  The bucket is handed to autograd as the gradient tensors
+    themselves, and autograd installs them as p.grad WITHOUT a copy; if a p.grad from an earlier backward is still
+    alive (zero_grad(set_to_none=False), gradient accumulation) it may BE the bucket, and the next backward would
+    overwrite it before AccumulateGrad adds the new gradient to it (a silent 2x).  So the bucket is only used when
+    every parameter of its owner has p.grad None; otherwise the gradients go to a fresh allocation and the owner's
+    step() copies them in."""
+    entry = grad_buckets.get(params[0][0].data_ptr())
+    if entry is None:
+        return None
+    bucket, owner = entry
+    opt = owner() if owner is not None else None
+    if opt is not None and any(q.grad is not None for g in opt.param_groups for q in g['params']):
+        return None
+    return bucket
 
 
 def _alloc_grads(params):
     """Gradient buffers for every layer as consecutive views of ONE flat tensor, in parameter order, so a
     multi-GPU step can all-reduce them with a single collective and no copies (parallel.py)."""
     total = sum(t.numel() for p in params for t in p)
-    bucket = grad_buckets.get(params[0][0].data_ptr())
+    bucket = _bucket_for(params)
     if bucket is not None and bucket.numel() >= total and bucket.device == params[0][0].device:
         flat = bucket[:total]
     else:
@@ -419,6 +437,11 @@ class _FusedELBO(torch.autograd.Function):
         prior, S, beta, tf32, eps, nl = ctx.cfg
         if g_loss is None:
             return (None,) * (9 + 4 * nl)
+        if getattr(ctx, 'consumed', False):
+            # the split-K backward kernels ADD into the dx workspace zero-filled by the forward (BBB_F_OUT_ZEROED)
+            raise RuntimeError('sample_elbo: this graph was already differentiated (retain_graph=True is not '
+                               'supported by the fused ELBO path: its backward workspace is single-use)')
+        ctx.consumed = True
         sv = ctx.saved_tensors
         x2, d_out = sv[0], sv[1]
         params = [tuple(_f32c(t) for t in sv[2 + 4 * i:6 + 4 * i]) for i in range(nl)]

@@ -42,6 +42,7 @@ class GraphedTrainStep:
         params = [p for g in optimizer.param_groups for p in g['params']]
         p_snap = [p.detach().clone() for p in params]
         s_snap = {id(t): t.clone() for st in optimizer.state.values() for t in st.values() if torch.is_tensor(t)}
+        t_base = getattr(optimizer, '_t', 0)       # steps already taken eagerly: the captured launch continues from them
         R.use_device_step(self.counter)
         try:
             side = torch.cuda.Stream()
@@ -53,7 +54,7 @@ class GraphedTrainStep:
             torch.cuda.synchronize()
             self.counter.zero_()
             if hasattr(optimizer, '_t'):
-                optimizer._t = 0                 # the captured launch bakes host step 1; the device counter adds replays
+                optimizer._t = t_base            # the captured launch bakes host step t_base + 1; the device counter adds replays
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.loss_info = self._step()
@@ -67,6 +68,8 @@ class GraphedTrainStep:
                     if torch.is_tensor(t):
                         t.copy_(s_snap[id(t)]) if id(t) in s_snap else t.zero_()
         self.counter.zero_()
+        if hasattr(optimizer, '_t'):
+            optimizer._t = t_base
         torch.cuda.synchronize()
 
     def _step(self):

@@ -192,9 +192,9 @@ class MLP_Dropout(nn.Module):
         self.hidden_units = model_params['hidden_units']
         self.mode = model_params['mode']
         self.net = nn.Sequential(nn.Linear(self.input_shape, self.hidden_units), nn.ReLU(),
-                                 nn.Dropout(model_params['dropout']),
+                                 nn.Dropout(0.5),      # fixed, as the reference (networks.py:268,271); the callers'
                                  nn.Linear(self.hidden_units, self.hidden_units), nn.ReLU(),
-                                 nn.Dropout(model_params['dropout']),
+                                 nn.Dropout(0.5),      # 'dropout' key is a boolean routing flag, not a probability
                                  nn.Linear(self.hidden_units, self.classes))
 
     def forward(self, x):

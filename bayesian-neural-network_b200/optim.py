@@ -3,6 +3,7 @@ kernel launch (csrc/bbb_adam.cu).  Opt-in: the reference's callers 
 torch.optim.Adam; GraphedTrainStep and bench.py use this one because the stock foreach implementation costs
 more than the whole fused forward+backward at the MNIST-shape config."""
 import ctypes as C
+import weakref
 
 import torch
 
@@ -45,6 +46,18 @@ class FusedAdam(torch.optim.Optimizer):
         d.lr_scale_dev = L.ptr(self.lr_scale_dev)
         return d
 
+    def _mirror_step(self):
+        """torch.optim.Adam keeps the step count in state[p]['step']: mirror ours there so a state_dict round trip
+        (or handing the state to torch.optim.Adam) continues the bias correction instead of restarting it."""
+        for st in self.state.values():
+            if 'step' in st:
+                st['step'].fill_(float(self._t))
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        steps = [float(st['step']) for st in self.state.values() if 'step' in st]
+        self._t = int(max(steps)) if steps else 0
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -53,6 +66,7 @@ class FusedAdam(torch.optim.Optimizer):
             ps = [p for p in group['params'] if p.grad is not None]
             for i in range(0, len(ps), 32):
                 self._launch(group, ps[i:i + 32])
+        self._mirror_step()
         return loss
 
     def _launch(self, group, ps):
@@ -160,8 +174,10 @@ class PeerShardedAdam(torch.optim.Optimizer):
                 st['exp_avg_sq'] = self.flat_v[off:off + k].view(p.shape)
                 self.offsets.append(off)
                 off += k
-        F.grad_buckets[self.flat_p.data_ptr()] = self.flat_g    # this network's backward writes its gradients here
+        # this network's backward writes its gradients here (only while no p.grad is alive: functional._bucket_for)
+        F.grad_buckets[self.flat_p.data_ptr()] = (self.flat_g, weakref.ref(self))
         if self.world > 1:
+            dist.broadcast(self.flat_p, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             self.peer_p = open_peers(self.flat_p, group)
             self.peer_g = open_peers(self.flat_g, group)
             self.peer_f = open_peers(self.flags, group)
@@ -175,6 +191,15 @@ class PeerShardedAdam(torch.optim.Optimizer):
 
     def use_device_step(self, counter):
         self.step_dev = counter
+
+    def zero_grad(self, set_to_none=True):
+        """Always drops the gradients: a p.grad kept alive would alias the shared bucket (functional._bucket_for)."""
+        super().zero_grad(set_to_none=True)
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        steps = [float(st['step']) for st in self.state.values() if 'step' in st]
+        self._t = int(max(steps)) if steps else 0
 
     def release(self):
         """Stop routing this network's gradients into the shared bucket (the mapped peer memory itself stays mapped
@@ -208,4 +233,6 @@ class PeerShardedAdam(torch.optim.Optimizer):
                                            float(group['lr']), float(b1), float(b2), float(group['eps']), self._t,
                                            L.ptr(self.step_dev), L.ptr(self.lr_scale_dev), L.stream()),
                 'bbb_adam_step_peer')
+        for st in self.state.values():
+            st['step'].fill_(float(self._t))
         return loss

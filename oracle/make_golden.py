@@ -51,6 +51,14 @@ CASES = [
     dict(name='cfg4_bandit', kind='ws', mode='regression', dims=[119, 100, 100, 1], B=64, S=2,
          prior_init=[0.5, -0, -6], mixture=True, sigma=1.0, M=64, idx=0, full=False, flat_target=True,
          bandit_data=True),
+    # Nets deeper than the reference's fixed three layers (BASELINE.json config 5 is 4 x 4096 hidden): the reference's
+    # own BayesianLinear layers (networks.py:48-88) composed by hand, driven by the loop of networks.py:199-208.
+    dict(name='deep5_small_mix', kind='ws', mode='classification', dims=[16, 12, 10, 12, 10, 4], B=6, S=3,
+         prior_init=[0.5, -0, -6], mixture=True, sigma=1.0, M=4, idx=1, full=True, img=(1, 4, 4)),
+    # a scaled config 5 that runs the batch-resident kernels (batch >= 384, widths >= 256) with ragged tails:
+    # batch 640 = 512 + 128, widths that are not multiples of 128, three samples (one odd sample group)
+    dict(name='deep5_cfg5_scaled', kind='ws', mode='classification', dims=[320, 384, 264, 392, 256, 10], B=640, S=3,
+         prior_init=[0.5, -0, -6], mixture=True, sigma=1.0, M=4, idx=0, full=False, randn_x=True),
 ]
 MU_INIT, RHO_INIT = [-0.2, 0.2], [-5, -4]
 
@@ -71,7 +79,10 @@ def make_data(case):
     """Synthetic inputs of the config's shape, drawn after manual_seed(SEED_DATA)."""
     torch.manual_seed(SEED_DATA)
     B, dims = case['B'], case['dims']
-    if case['mode'] == 'classification':
+    if case['mode'] == 'classification' and case.get('randn_x'):
+        x = torch.randn(B, dims[0])          # config 5: x ~ N(0,1) [B, d_in] (SURVEY 8d)
+        y = torch.randint(0, dims[-1], (B,))
+    elif case['mode'] == 'classification':
         x = torch.rand(B, *case['img'])
         y = torch.randint(0, dims[-1], (B,))
     elif case.get('reg_data'):
@@ -88,13 +99,60 @@ def make_data(case):
     return x, y
 
 
+def build_deep_reference(refnet, case):
+    """A network of len(dims)-1 reference BayesianLinear layers (networks.py:48-88) with ReLU between them and
+    the reference's own sample_elbo / get_nll (networks.py:183-209) bound to it: BayesianNetwork.__init__ is
+    fixed at three layers (networks.py:160-164), everything else of the class is depth-agnostic once
+    forward / log_prior / log_variational_posterior walk the layer list."""
+    dims = case['dims']
+
+    class DeepReference(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mode, self.local_reparam = case['mode'], False
+            self.input_shape, self.classes = dims[0], dims[-1]
+            self.n_layers = len(dims) - 1
+            for i in range(self.n_layers):          # constructor draw order = layer order (networks.py:53-58)
+                setattr(self, f'l{i + 1}', refnet.BayesianLinear(dims[i], dims[i + 1], MU_INIT, RHO_INIT,
+                                                                 case['prior_init'], case['mixture']))
+
+        def layers(self):
+            return [getattr(self, f'l{i + 1}') for i in range(self.n_layers)]
+
+        def forward(self, x, sample=False):          # networks.py:166-172 with the layer list
+            if self.mode == 'classification':
+                x = x.view(-1, self.input_shape)
+            for i, l in enumerate(self.layers()):
+                x = l(x, sample)
+                if i + 1 < self.n_layers:
+                    x = torch.relu(x)
+            return x
+
+        def log_prior(self):                         # networks.py:174-175
+            return sum(l.log_prior for l in self.layers())
+
+        def log_variational_posterior(self):         # networks.py:177-178
+            return sum(l.log_variational_posterior for l in self.layers())
+
+        get_nll = refnet.BayesianNetwork.get_nll              # networks.py:183-190, unmodified
+        sample_elbo = refnet.BayesianNetwork.sample_elbo      # networks.py:192-209, unmodified
+    return DeepReference()
+
+
 def run_case(refnet, case):
     dims = case['dims']
+    if len(dims) != 4:
+        torch.manual_seed(SEED_PARAMS)
+        return record_case(case, build_deep_reference(refnet, case))
     model_params = dict(input_shape=dims[0], classes=dims[-1], batch_size=case['B'], hidden_units=dims[1],
                         mode=case['mode'], mu_init=MU_INIT, rho_init=RHO_INIT, prior_init=case['prior_init'],
                         mixture_prior=case['mixture'], local_reparam=(case['kind'] == 'lr'))
     torch.manual_seed(SEED_PARAMS)
-    net = refnet.BayesianNetwork(model_params)
+    return record_case(case, refnet.BayesianNetwork(model_params))
+
+
+def record_case(case, net):
+    dims = case['dims']
     x, y = make_data(case)
     beta = 2 ** (case['M'] - (case['idx'] + 1)) / (2 ** case['M'] - 1)
 
@@ -130,7 +188,7 @@ def run_case(refnet, case):
         rec['nll'] = info[3].detach().numpy().reshape(-1)
     out = torch.stack(outs).numpy()
     names = []
-    for li, layer in enumerate((net.l1, net.l2, net.l3)):
+    for li, layer in enumerate([getattr(net, f'l{i + 1}') for i in range(len(dims) - 1)]):
         for pn in ('weight_mu', 'weight_rho', 'bias_mu', 'bias_rho'):
             p = getattr(layer, pn)
             key = f'l{li + 1}.{pn}'
@@ -181,6 +239,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default=os.environ.get('BNN_REFERENCE_PATH', '/root/reference'))
     ap.add_argument('--out', default=os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden'))
+    ap.add_argument('--only', nargs='*', default=None, help='case names to (re)generate; default: all')
     args = ap.parse_args()
     out_dir = os.path.abspath(args.out)
     os.makedirs(out_dir, exist_ok=True)
@@ -191,6 +250,8 @@ def main():
         try:
             refnet = load_reference(args.reference)
             for case in CASES:
+                if args.only and case['name'] not in args.only:
+                    continue
                 rec = run_case(refnet, case)
                 path = os.path.join(out_dir, case['name'] + '.npz')
                 np.savez_compressed(path, **rec)

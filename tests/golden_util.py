@@ -13,6 +13,8 @@ SMALL = ['small_reg_mix', 'small_cls_mix', 'small_cls_gauss', 'small_bandit_bcas
 SMALL_LR = ['small_lr_cls', 'small_lr_reg']
 BIG = ['cfg1_reg_mix', 'cfg4_bandit', 'cfg2_mnist_mix']
 BIG_LR = ['cfg3_mnist_lr']
+DEEP_SMALL = ['deep5_small_mix']          # five reference BayesianLinear layers composed by hand, fully stored
+DEEP_BIG = ['deep5_cfg5_scaled']          # scaled BASELINE.json config 5: runs the batch-resident kernels
 PNAMES = ('weight_mu', 'weight_rho', 'bias_mu', 'bias_rho')
 
 
@@ -48,7 +50,8 @@ class Case:
 
     def model_params(self):
         d = self.dims
-        return dict(input_shape=d[0], classes=d[-1], batch_size=self.B, hidden_units=d[1], mode=self.mode,
+        hidden = d[1] if len(d) == 4 else list(d[1:-1])
+        return dict(input_shape=d[0], classes=d[-1], batch_size=self.B, hidden_units=hidden, mode=self.mode,
                     mu_init=MU_INIT, rho_init=RHO_INIT, prior_init=self.prior_init,
                     mixture_prior=self.mixture, local_reparam=self.lr)
 

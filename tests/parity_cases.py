@@ -117,7 +117,7 @@ def check_state_dict(case, device):
     """State-dict keys/shapes the reference's load_model_utils.py / weight_pruning.py rely on."""
     net = build_net(case, device)
     keys = list(net.state_dict().keys())
-    assert keys == [f'l{i}.{pn}' for i in (1, 2, 3) for pn in PNAMES]
+    assert keys == [f'l{i + 1}.{pn}' for i in range(len(case.layers)) for pn in PNAMES]
     d = case.dims
     want = (d[0], d[1]) if case.lr else (d[1], d[0])
     assert tuple(net.l1.weight_mu.shape) == want
@@ -125,21 +125,35 @@ def check_state_dict(case, device):
 
 
 def check_batched_prediction(case, device, samples=4, rtol=1e-5):
-    """net.sample_predict (one launch per layer for all sampled forwards) == the reference's loop of
-    net(x, sample=True) calls in eval mode, same seed."""
+    """net.sample_predict (one launch per layer for all sampled forwards) and net.predict_proba against the ORACLE:
+    `samples` sampled forwards of the reference's layers (networks.py:73-88 / 116-138) with the reference's eps draw
+    order, softmax-averaged as class_task.py:81-87 does.  Also == the repo's own loop of
+    net(x, sample=True) calls in eval mode (the call pattern of the reference's predict / evaluate)."""
+    from oracle import bbb_oracle as O
     net = build_net(case, device)
     net.eval()
     x = case.x.to(device)
+    with torch.no_grad():
+        with torch.random.fork_rng():
+            torch.manual_seed(123)
+            eps = O.draw_eps(case.dims, samples, batch=case.B, local_reparam=case.lr)
+        if case.lr:
+            want = torch.stack([O.mlp_forward_lr(case.x, case.layers, case.prior[1], eps[s], case.mode, calc_kl=False)[0]
+                                for s in range(samples)])
+        else:
+            want = torch.stack([O.mlp_forward(case.x, case.layers, case.prior, eps[s], case.mode,
+                                              calc_log_probs=False)[0] for s in range(samples)])
     with torch.no_grad(), bnn_b200.eps_mode('reference'):
         torch.manual_seed(123)
-        want = torch.stack([net(x, sample=True) for _ in range(samples)])
+        loop = torch.stack([net(x, sample=True) for _ in range(samples)])
         torch.manual_seed(123)
         got = net.sample_predict(x, samples)
     assert tuple(got.shape) == tuple(want.shape)
-    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=rtol, atol=1e-6)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=rtol, atol=2e-6)
+    np.testing.assert_allclose(loop.cpu().numpy(), want.numpy(), rtol=rtol, atol=2e-6)
     if case.mode == 'classification':
         with torch.no_grad(), bnn_b200.eps_mode('reference'):
             torch.manual_seed(123)
             p = net.predict_proba(x, samples)
         np.testing.assert_allclose(p.sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
-        np.testing.assert_allclose(p.cpu().numpy(), torch.softmax(want, -1).mean(0).cpu().numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(p.cpu().numpy(), torch.softmax(want, -1).mean(0).numpy(), rtol=1e-4, atol=1e-6)

@@ -14,29 +14,29 @@ from bnn_b200 import functional as F
 from oracle import bbb_oracle as O
 from oracle import closed_form as CF
 from tests import parity_cases as PC
-from tests.golden_util import Case, SMALL, SMALL_LR, BIG, BIG_LR, PNAMES
+from tests.golden_util import Case, SMALL, SMALL_LR, BIG, BIG_LR, DEEP_SMALL, DEEP_BIG, PNAMES
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
-@pytest.mark.parametrize('name', SMALL + SMALL_LR + BIG + BIG_LR)
+@pytest.mark.parametrize('name', SMALL + SMALL_LR + BIG + BIG_LR + DEEP_SMALL + DEEP_BIG)
 @pytest.mark.parametrize('fused', [True, False])
 def test_train_step_matches_reference(name, fused):
     PC.check_train_step(Case(name), DEV, fused=fused)
 
 
-@pytest.mark.parametrize('name', SMALL + SMALL_LR + ['cfg4_bandit'])
+@pytest.mark.parametrize('name', SMALL + SMALL_LR + DEEP_SMALL + ['cfg4_bandit'])
 def test_layer_level_api_matches_reference(name):
     PC.check_layerwise_train_step(Case(name), DEV)
 
 
-@pytest.mark.parametrize('name', SMALL + SMALL_LR)
+@pytest.mark.parametrize('name', SMALL + SMALL_LR + DEEP_SMALL)
 def test_eval_modes(name):
     PC.check_eval_modes(Case(name), DEV)
 
 
-@pytest.mark.parametrize('name', SMALL + SMALL_LR + ['cfg4_bandit'])
+@pytest.mark.parametrize('name', SMALL + SMALL_LR + DEEP_SMALL + ['cfg4_bandit'])
 def test_batched_prediction(name):
     PC.check_batched_prediction(Case(name), DEV)
 
@@ -114,7 +114,7 @@ def _philox_eps_for(dims, S, seed, step, sample_base=0, lr_batch=None):
 
 
 @pytest.mark.parametrize('name', ['small_cls_mix', 'small_bandit_bcast', 'cfg4_bandit', 'cfg2_mnist_mix',
-                                  'small_lr_reg', 'cfg3_mnist_lr'])
+                                  'small_lr_reg', 'cfg3_mnist_lr', 'deep5_small_mix'])
 def test_philox_mode_equals_injecting_the_same_stream(name):
     """In-kernel eps (forward AND the backward's regeneration) == the fill kernel's stream injected
     through the parity path.  Covers aligned (vectorised) and ragged (119, 1, 9 wide) rows."""
@@ -154,7 +154,7 @@ def test_philox_mode_equals_injecting_the_same_stream(name):
     else:
         r = CF.elbo_step(xx, yy, layers, c.prior, eps_np, c.beta, c.mode, c.sigma)
     assert abs(float(info[0].detach()) - r['loss']) <= 1e-5 * abs(r['loss'])
-    for li in range(3):
+    for li in range(len(c.layers)):
         for pi in range(4):
             ref = r['grads'][li][pi]
             err = np.abs(g1[li][pi] - ref).max() / np.abs(ref).max()
@@ -201,7 +201,7 @@ def test_sample_sharding_is_invariant():
     b_s, b_g = run(2, 2)
     np.testing.assert_allclose(torch.cat([a_s[:2], b_s[:2], a_s[2:], b_s[2:]]).cpu().numpy(), full_s.cpu().numpy(),
                                rtol=1e-6)
-    for li in range(3):
+    for li in range(len(c.layers)):
         for pi in range(4):
             tot = a_g[li][pi] + b_g[li][pi]
             assert np.abs(tot - full_g[li][pi]).max() <= 2e-6 * np.abs(full_g[li][pi]).max()

@@ -10,7 +10,7 @@ import torch
 
 import bnn_b200
 from tests import parity_cases as PC
-from tests.golden_util import Case, SMALL, BIG, SMALL_LR, BIG_LR
+from tests.golden_util import Case, SMALL, BIG, SMALL_LR, BIG_LR, DEEP_SMALL, DEEP_BIG
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -32,7 +32,7 @@ def test_tcgen05_plain_gemm(B, d_in, d_out):
     assert err < 2e-3, float(err)
 
 
-@pytest.mark.parametrize('name', SMALL + BIG + SMALL_LR + BIG_LR)
+@pytest.mark.parametrize('name', SMALL + BIG + SMALL_LR + BIG_LR + DEEP_SMALL + DEEP_BIG)
 @pytest.mark.parametrize('fused', [True, False])
 def test_tf32_train_step_matches_reference(name, fused):
     c = Case(name)

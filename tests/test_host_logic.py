@@ -10,7 +10,7 @@ import torch
 
 import bnn_b200
 from tests import fake_bbb, parity_cases as PC
-from tests.golden_util import Case, SMALL, SMALL_LR
+from tests.golden_util import Case, SMALL, SMALL_LR, DEEP_SMALL
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -20,7 +20,7 @@ def fake(monkeypatch):
     return fake_bbb.install(monkeypatch)
 
 
-@pytest.mark.parametrize('name', SMALL + SMALL_LR + ['cfg4_bandit'])
+@pytest.mark.parametrize('name', SMALL + SMALL_LR + DEEP_SMALL + ['cfg4_bandit'])
 @pytest.mark.parametrize('fused', [True, False])
 def test_train_step_network_level(fake, name, fused):
     PC.check_train_step(Case(name), 'cpu', fused=fused)
@@ -40,7 +40,7 @@ def test_eval_modes(fake, name):
     PC.check_eval_modes(Case(name), 'cpu')
 
 
-@pytest.mark.parametrize('name', ['small_cls_mix', 'small_lr_cls'])
+@pytest.mark.parametrize('name', ['small_cls_mix', 'small_lr_cls', 'deep5_small_mix'])
 def test_state_dict_layout(fake, name):
     PC.check_state_dict(Case(name), 'cpu')
 
@@ -138,6 +138,30 @@ def test_peer_sharded_adam_single_rank_is_adam(fake):
         for p, q in zip(ref_net.parameters(), net.parameters()):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), float((p - q).abs().max())
             assert torch.allclose(ref.state[p]['exp_avg_sq'], opt.state[q]['exp_avg_sq'], rtol=1e-5, atol=1e-12)
+    finally:
+        F.grad_buckets.clear()
+
+
+def test_gradient_bucket_is_not_used_while_a_grad_is_alive(fake):
+    """A p.grad kept alive across steps (zero_grad(set_to_none=False), gradient accumulation) must not alias the
+    persistent bucket the next backward writes into: accumulating two backwards gives exactly twice the gradient."""
+    from bnn_b200 import functional as F
+    c = Case('small_cls_mix')
+    net = PC.build_net(c, 'cpu').train()
+    try:
+        opt = bnn_b200.PeerShardedAdam(net.parameters(), lr=1e-3)
+        grads = []
+        with bnn_b200.eps_mode('reference'):
+            for it in range(2):                      # two backwards, no zero_grad in between: accumulation
+                torch.manual_seed(5)
+                net.sample_elbo(c.x, c.y, c.beta, c.S)[0].backward()
+                grads.append(net.l1.weight_mu.grad.detach().clone())
+        assert torch.allclose(grads[1], 2 * grads[0], rtol=1e-6, atol=1e-9)
+        torch.nn.Module.zero_grad(net, set_to_none=False)             # grads stay alive, zero-filled
+        with bnn_b200.eps_mode('reference'):
+            torch.manual_seed(5)
+            net.sample_elbo(c.x, c.y, c.beta, c.S)[0].backward()
+        assert torch.allclose(net.l1.weight_mu.grad, grads[0], rtol=1e-6, atol=1e-9)
     finally:
         F.grad_buckets.clear()
 

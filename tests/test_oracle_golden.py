@@ -6,7 +6,7 @@ import torch
 
 from oracle import bbb_oracle as O
 from oracle import closed_form as CF
-from tests.golden_util import Case, SMALL, SMALL_LR, BIG, BIG_LR
+from tests.golden_util import Case, SMALL, SMALL_LR, BIG, BIG_LR, DEEP_SMALL, DEEP_BIG
 
 RTOL_F32 = 2e-6      # same op order as the reference => round-off only
 RTOL_CF = 1e-5       # float64 closed form vs the reference's fp32 autograd; gradients additionally get the
@@ -17,7 +17,7 @@ def _leaf(layers):
     return [tuple(p.clone().requires_grad_(True) for p in layer) for layer in layers]
 
 
-@pytest.mark.parametrize('name', SMALL + BIG)
+@pytest.mark.parametrize('name', SMALL + BIG + DEEP_SMALL + DEEP_BIG)
 def test_torch_oracle_weight_sampling(name):
     c = Case(name)
     torch.set_num_threads(1)
@@ -42,7 +42,7 @@ def test_torch_oracle_local_reparam(name):
     c.check_grads([[p.grad.numpy() for p in layer] for layer in layers], RTOL_F32 * 5)
 
 
-@pytest.mark.parametrize('name', SMALL)
+@pytest.mark.parametrize('name', SMALL + DEEP_SMALL)
 def test_torch_oracle_eval_modes(name):
     c = Case(name)
     with torch.no_grad():
@@ -72,7 +72,7 @@ def _np_eps(eps):
     return [[(a.double().numpy(), b.double().numpy()) for a, b in per] for per in eps]
 
 
-@pytest.mark.parametrize('name', SMALL + ['cfg4_bandit', 'cfg1_reg_mix'])
+@pytest.mark.parametrize('name', SMALL + DEEP_SMALL + ['cfg4_bandit', 'cfg1_reg_mix'])
 def test_closed_form_weight_sampling(name):
     c = Case(name)
     r = CF.elbo_step(c.x.double().numpy(), c.y.numpy() if c.mode == 'classification' else c.y.double().numpy(),

@@ -94,6 +94,28 @@ def _drive_bandit(dev):
     assert len(agent.cumulative_regrets) == 11
 
 
+def _drive_mc_dropout(dev):
+    """The MC-dropout baselines (reg_task.py:142-183, class_task.py:185-240) construct networks.MLP_Dropout with no
+    'dropout' key (regression) or 'dropout': True (classification); the reference hard-codes p = 0.5."""
+    reg = importlib.import_module('regression.reg_task')
+    cls = importlib.import_module('classification.class_task')
+    rp = dict(batch_size=16, num_batches=2, test_samples=4, x_shape=1, y_shape=1, lr=1e-3, save_dir='./saved_models',
+              hidden_units=24, mode='regression')
+    task = reg.MCDropout_Regression('t', rp)
+    g = torch.Generator().manual_seed(0)
+    data = [(torch.randn(16, 1, generator=g), torch.randn(16, 1, generator=g)) for _ in range(2)]
+    task.train_step(data)
+    assert torch.isfinite(task.loss_info).all()
+    cp = dict(lr=1e-3, hidden_units=32, mode='classification', batch_size=8, num_batches=3, test_samples=3, x_shape=16,
+              classes=5, save_dir='./saved_models', dropout=True)
+    ctask = cls.MCDropout_Classification('t', cp)
+    drops = [m for m in ctask.net.modules() if isinstance(m, torch.nn.Dropout)]
+    assert len(drops) == 2 and all(m.p == 0.5 for m in drops)
+    ctask.net.train()
+    out = ctask.net(torch.rand(8, 1, 4, 4).to(dev))
+    assert out.shape == (8, 5) and torch.isfinite(out).all() and out.abs().max() > 0
+
+
 def _cpu_double(monkeypatch):
     """No GPU here: the C ABI is the test double, which needs eps injected (the reference's own CPU draws)."""
     import bnn_b200
@@ -117,6 +139,11 @@ def test_reference_classification_task_on_dropin_cpu_double(ref, monkeypatch, lo
 def test_reference_bandit_on_dropin_cpu_double(ref, monkeypatch):
     _cpu_double(monkeypatch)
     _drive_bandit('cpu')
+
+
+def test_reference_mc_dropout_baselines_on_dropin(ref, monkeypatch):
+    _cpu_double(monkeypatch)
+    _drive_mc_dropout('cpu')
 
 
 @pytest.mark.gpu
