@@ -228,7 +228,7 @@ extern "C" int bbb_adam_step_peer(const bbb_peer_comm *comm, float *exp_avg, flo
   // must make progress independently: at most 4 blocks per SM, so the grid is always co-resident
   const int64_t slice_q = (n >> 2) / comm->world + 1;
   int64_t blocks = (slice_q + 255) / 256;
-  const int64_t cap = (int64_t)kSMs * 4;
+  const int64_t cap = (int64_t)sm_count() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   BBB_CHECK_CUDA(launch_pdl(peer_adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a));
@@ -262,7 +262,7 @@ extern "C" int bbb_adam_step(int32_t n_tensors, float *const *params, const floa
   a.n = n; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = (float)eps; a.step = step; a.step_dev = step_dev;
   a.lr_scale_dev = lr_scale_dev;
   int64_t blocks = (q + 255) / 256;
-  const int64_t cap = (int64_t)kSMs * 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   BBB_CHECK_CUDA(launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a));
   BBB_CHECK_LAUNCH();

@@ -62,7 +62,18 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // constants
 // ---------------------------------------------------------------------------------------
 constexpr float kHalfLog2Pi = 0.918938533204672741780329736406f;
-constexpr int kSMs = 148;  // B200
+// SM count of the CURRENT device (148 on B200), queried once per device: grids are sized from it
+inline int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cached[dev];
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;   // benign race: every thread writes the same value
+  }
+  return n;
+}
 
 // Prior descriptor with the per-call constants folded on the host.
 struct PriorDev {

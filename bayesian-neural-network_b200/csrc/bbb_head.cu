@@ -883,7 +883,7 @@ int launch_linear_bwd_head(const LinArgs &a, cudaStream_t st) {
     rbp = (int)a.B;
   }
   // about one column range per SM; the (sample, o, quad) items of a pass must fit the 64 item slots
-  int wq = cdiv_i(nq_i, kSMs);
+  int wq = cdiv_i(nq_i, sm_count());
   int cap = SLOTS / (spp * (int)a.out);
   while (cap < 1) { --spp; cap = SLOTS / (spp * (int)a.out); }   // out = 16 with 4 samples: fewer samples per pass
   if (wq > cap) wq = cap;
@@ -907,7 +907,7 @@ int launch_lr_bwd_head(const LrArgs &a, cudaStream_t st) {
     if (spp > a.S) spp = a.S;
     rbp = (int)a.B;
   }
-  int wq = cdiv_i(nq_i, kSMs);               // about one range of weight rows per SM; w * out <= 256 item threads
+  int wq = cdiv_i(nq_i, sm_count());               // about one range of weight rows per SM; w * out <= 256 item threads
   int cap = HT / (4 * (int)a.out);
   if (cap < 1) cap = 1;
   if (wq > cap) wq = cap;

@@ -406,7 +406,7 @@ int launch_linear_bwd_fused(const LinArgs &a, cudaStream_t st) {
   const int n_ot = cdiv_i(a.out, 128);
   const int T_o = ((cdiv_i(a.out, n_ot) + 3) / 4) * 4;         // equal row tiles; a multiple of 4 keeps dz loads vectorised
   const int nq_i = (int)(a.in / 4);
-  int n_c = kSMs / n_ot;                                       // about one CTA per SM
+  int n_c = sm_count() / n_ot;                                       // about one CTA per SM
   const int need = cdiv_i(nq_i, wmax_of(XW_MAX) / 4);          // every column range must fit the widest window
   if (n_c < need) n_c = need;
   if (n_c > nq_i) n_c = nq_i;

@@ -458,7 +458,7 @@ bool linear_narrow_supported(const LinArgs &a) {
 
 int launch_linear_fwd_narrow(const LinArgs &a, cudaStream_t st) {
   // about two CTAs per SM over (row groups x samples), at least 8 rows (one per warp) each
-  int rows = cdiv_i(a.B * a.S, 2 * kSMs);
+  int rows = cdiv_i(a.B * a.S, 2 * sm_count());
   rows = ((rows < 8 ? 8 : rows) + 7) / 8 * 8;
   dim3 grid(cdiv_i(a.B, rows), (unsigned)a.S);
   const size_t smem = (size_t)a.in * a.out * sizeof(float);
@@ -475,7 +475,7 @@ int launch_linear_fwd_narrow(const LinArgs &a, cudaStream_t st) {
 
 int launch_linear_bwd_narrow(const LinArgs &a, cudaStream_t st) {
   const int nq_i = (int)(a.in / 4);
-  int wq = cdiv_i(nq_i, kSMs);           // about one column range per SM, at most 32 columns
+  int wq = cdiv_i(nq_i, sm_count());           // about one column range per SM, at most 32 columns
   if (wq > 8) wq = 8;
   if (wq < 1) wq = 1;
   BBB_CHECK_CUDA(launch_pdl(narrow_bwd_kernel, dim3(cdiv_i(nq_i, wq)), dim3(NTH), 0, st, a, wq));
@@ -489,7 +489,7 @@ bool lr_narrow_supported(const LrArgs &a) {
 }
 
 int launch_lr_fwd_narrow(const LrArgs &a, cudaStream_t st) {
-  int rows = cdiv_i(a.B * a.S, 2 * kSMs);
+  int rows = cdiv_i(a.B * a.S, 2 * sm_count());
   rows = ((rows < 64 ? 64 : rows) + 31) / 32 * 32;      // >= 2 rows per warp: the weight staging is per CTA
   dim3 grid(cdiv_i(a.B, rows), (unsigned)a.S);
   const size_t smem = 2 * (size_t)a.in * a.out * sizeof(float);
@@ -500,7 +500,7 @@ int launch_lr_fwd_narrow(const LrArgs &a, cudaStream_t st) {
 }
 
 int launch_lr_bwd_narrow(const LrArgs &a, cudaStream_t st) {
-  int wrows = cdiv_i(a.in, kSMs);        // about one range of weight rows per SM
+  int wrows = cdiv_i(a.in, sm_count());        // about one range of weight rows per SM
   const int cap = NTH / (int)a.out < 32 ? NTH / (int)a.out : 32;   // one thread per owned weight
   if (wrows > cap) wrows = cap;
   if (wrows < 1) wrows = 1;

@@ -310,7 +310,7 @@ int set_smem(K kernel, int bytes) {
   return BBB_OK;
 }
 
-inline int grid_for(int total_units) { return total_units < kCtaPerSm * kSMs ? total_units : kCtaPerSm * kSMs; }
+inline int grid_for(int total_units) { return total_units < kCtaPerSm * sm_count() ? total_units : kCtaPerSm * sm_count(); }
 
 template <int BN, int SG>
 int launch_fwd(const LinArgs &a, cudaStream_t st) {

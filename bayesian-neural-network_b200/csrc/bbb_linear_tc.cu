@@ -463,7 +463,7 @@ inline int cdiv_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // K split so that the grid is about one wave of the 148 SMs; chunk is a multiple of 32
 inline void pick_ksplit(int64_t K, int tiles, int *k_chunk, int *n_ksplit) {
   const int nkb = cdiv_i(K, BK);
-  int want = tiles >= kSMs ? 1 : (kSMs + tiles / 2) / tiles;  // about one CTA per SM: every split costs a red pass
+  int want = tiles >= sm_count() ? 1 : (sm_count() + tiles / 2) / tiles;  // about one CTA per SM: every split costs a red pass
   if (want > nkb) want = nkb;
   if (want < 1) want = 1;
   const int per = cdiv_i(nkb, want);

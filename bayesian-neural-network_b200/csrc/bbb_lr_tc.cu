@@ -610,7 +610,7 @@ int launch_lr_fwd_tc(const LrArgs &a, cudaStream_t st) {
   const bool sample = a.flags & BBB_F_SAMPLE;
   const int o_tiles = cdiv_i(a.out, BN), nkb = cdiv_i(a.in, BK);
   const int total = (int)a.S * o_tiles * nkb;
-  const int grid = total < kCtaPerSm * kSMs ? total : kCtaPerSm * kSMs;
+  const int grid = total < kCtaPerSm * sm_count() ? total : kCtaPerSm * sm_count();
   if (!(a.flags & BBB_F_OUT_ZEROED)) {
     const size_t bytes = sizeof(float) * (size_t)a.S * a.B * a.out;
     BBB_CHECK_CUDA(cudaMemsetAsync(a.y, 0, bytes, st));
@@ -649,7 +649,7 @@ int launch_lr_bwd_tc(const LrArgs &a, cudaStream_t st) {
     }
     const int i_tiles = cdiv_i(a.in, BN), nkb = cdiv_i(a.out, BK);
     const int total = (int)a.S * i_tiles * nkb;
-    const int grid = total < kCtaPerSm * kSMs ? total : kCtaPerSm * kSMs;
+    const int grid = total < kCtaPerSm * sm_count() ? total : kCtaPerSm * sm_count();
     BBB_CHECK_CUDA(cudaFuncSetAttribute(lr_dgrad_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDyn));
     BBB_CHECK_CUDA(launch_pdl(lr_dgrad_sk_kernel, dim3(grid), dim3(NT2), kDyn, st, a, (const float *)dv, nkb, i_tiles, total));
     BBB_CHECK_LAUNCH();
@@ -658,7 +658,7 @@ int launch_lr_bwd_tc(const LrArgs &a, cudaStream_t st) {
   const int n_it = cdiv_i(a.in, 128);
   const int T_i = ((cdiv_i(a.in, n_it) + 3) / 4) * 4;
   const int nq_o = (int)(a.out / 4);
-  int n_c = kSMs / n_it;
+  int n_c = sm_count() / n_it;
   const int need = cdiv_i(nq_o, (WG_N - 8) / 4);
   if (n_c < need) n_c = need;
   if (n_c > nq_o) n_c = nq_o;

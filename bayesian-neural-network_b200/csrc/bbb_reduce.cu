@@ -181,7 +181,7 @@ __global__ void elbo_finalize_kernel(const double *logp, const double *logq, con
 
 inline int grid_for(int64_t work_items, int per_cta) {
   int64_t need = (work_items + per_cta - 1) / per_cta;
-  int64_t cap = (int64_t)kSMs * 8;  // 8 resident CTAs of 256 threads per SM
+  int64_t cap = (int64_t)sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }
