@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get('BBB_LIB') or os.path.join(_HERE, 'libbbb.so')   # BBB
 
 # flags (include/bbb.h)
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
-F_OUT_ZEROED, F_DX_PREACT = 256, 512
+F_OUT_ZEROED, F_DX_PREACT, F_RELU_OUT = 256, 512, 1024
 PRIOR_GAUSSIAN, PRIOR_MIXTURE = 0, 1
 NLL_NONE, NLL_CE, NLL_GAUSS = 0, 1, 2
 
@@ -37,6 +37,14 @@ class PeerComm(C.Structure):
                 ('flags', C.c_void_p * 8), ('epoch', C.c_void_p), ('done_blocks', C.c_void_p)]
 
 
+class MlpLayer(C.Structure):
+    """struct bbb_mlp_layer: one layer of a network-level call (bbb_mlp_fwd / bbb_mlp_bwd)"""
+    _fields_ = [('w_mu', C.c_void_p), ('w_rho', C.c_void_p), ('b_mu', C.c_void_p), ('b_rho', C.c_void_p),
+                ('eps_w', C.c_void_p), ('eps_b', C.c_void_p), ('inn', C.c_int64), ('out', C.c_int64),
+                ('y_pre', C.c_void_p), ('act', C.c_void_p), ('counters', C.c_void_p), ('dz', C.c_void_p),
+                ('g_w_mu', C.c_void_p), ('g_w_rho', C.c_void_p), ('g_b_mu', C.c_void_p), ('g_b_rho', C.c_void_p)]
+
+
 P, I64, I32, F32, F64, U32, U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_double, C.c_uint32, C.c_uint64
 _SIGS = {
     'bbb_version': ([], C.c_int),
@@ -57,6 +65,8 @@ _SIGS = {
     'bbb_nll_gauss': ([P, P, F32, I64, I64, I64, F32, P, P, P], C.c_int),
     'bbb_head_fwd': ([P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, I32, P, F32, F32, P, P, P, P, P, F32,
                       P, P, P, P], C.c_int),
+    'bbb_mlp_supported': ([P, I32, I64, I64, I32], C.c_int),
+    'bbb_mlp_fwd': ([P, I32, P, I64, I64, P, P, I32, I32, P, F32, F32, P, P, P, P, F32, P, P, P, P], C.c_int),
     'bbb_elbo_finalize': ([P, P, P, P, I64, F32, P, P, P], C.c_int),
     'bbb_adam_step': ([I32, P, P, P, P, P, F64, F64, F64, F64, U32, P, P, P], C.c_int),
     'bbb_enable_peer_access': ([I32], C.c_int),
@@ -82,6 +92,19 @@ def lib():
             fn.argtypes, fn.restype = argtypes, restype
         _lib = l
     return _lib
+
+
+_mlp_ok = {}
+
+
+def mlp_supported(dims, S, B, flags):
+    """bbb_mlp_supported, cached per (dims, S, B, flags)."""
+    key = (tuple(dims), S, B, flags)
+    ok = _mlp_ok.get(key)
+    if ok is None:
+        arr = (C.c_int64 * len(dims))(*dims)
+        ok = _mlp_ok[key] = bool(lib().bbb_mlp_supported(arr, len(dims) - 1, S, B, flags))
+    return ok
 
 
 def check(status, what):

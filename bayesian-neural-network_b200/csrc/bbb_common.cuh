@@ -108,6 +108,9 @@ inline PriorDev make_prior_dev(const bbb_prior *p) {
 
 struct RngDev {
   uint32_t key0, key1;  // seed
+  // the ten Philox round keys (key + r * Weyl constant), formed on the host: as kernel parameters they are constant-bank
+  // operands of the round's xor and cost neither a register nor the two additions per round
+  uint32_t rk0[10], rk1[10];
   uint32_t step;
   uint32_t sample_base;
   uint32_t tensor_w, tensor_b;
@@ -119,6 +122,8 @@ inline RngDev make_rng_dev(const bbb_rng *r) {
   if (r) {
     d.key0 = (uint32_t)(r->seed & 0xffffffffu);
     d.key1 = (uint32_t)(r->seed >> 32);
+    uint32_t k0 = d.key0, k1 = d.key1;
+    for (int i = 0; i < 10; ++i) { d.rk0[i] = k0; d.rk1[i] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
     d.step = r->step;
     d.sample_base = r->sample_base;
     d.tensor_w = 2u * r->layer;
@@ -134,33 +139,35 @@ inline RngDev make_rng_dev(const bbb_rng *r) {
 // on the element's linear index, never on the tiling, so forward and backward regenerate
 // bit-identical eps.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RngDev &rng) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += W0; k1 += W1;
+  for (int r = 0; r < 10; ++r) {   // 2 IMAD.WIDE + 2 LOP3 per round
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rng.rk0[r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rng.rk1[r];
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
   }
   return make_uint4(c0, c1, c2, c3);
 }
 
-__device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1]
-  return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+// low 23 bits of a Philox word -> float in [1, 2): (x & 0x7fffff) | 0x3f800000 as ONE lop3 (the 1.0f pattern is handed
+// over in a register so that the expression is not split into two immediates)
+__device__ __forceinline__ float bits_to_12(uint32_t x) {
+  uint32_t one, r;
+  asm("mov.b32 %0, 0x3f800000;" : "=r"(one));
+  asm("lop3.b32 %0, %1, 0x007fffff, %2, 0xEA;" : "=r"(r) : "r"(x), "r"(one));
+  return __uint_as_float(r);
 }
 
-// Box-Muller on the SFU: lg2 / sqrt / sin / cos approximations (abs error ~2^-21, far below the sampling
-// noise; moments and KS are checked in tests/test_gpu_parity.py).  ~12 instructions per pair.
+// Box-Muller on the SFU: lg2 / sqrt / sin / cos approximations (abs error ~2^-21, far below the sampling noise;
+// moments and KS are checked in tests/test_gpu_parity.py).  The uniforms carry 23 bits: u' = 2 - u in (0, 1] for the
+// radius (|z| <= 5.65), and sin / cos take 2 pi v with v in [1, 2) as it is (they are periodic).
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &z0, float &z1) {
-  const float u = u32_to_unit(a), v = u32_to_unit(b);
-  const float t = -2.0f * __logf(u);                 // >= 0
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  const float u = bits_to_12(a), v = bits_to_12(b);
+  float lg, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(2.0f - u));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));   // sqrt(-2 ln u')
   float s, c;
-  __sincosf(6.283185307179586f * v, &s, &c);         // argument in (0, 2 pi]
+  __sincosf(6.283185307179586f * v, &s, &c);
   z0 = r * s;
   z1 = r * c;
 }
@@ -173,7 +180,7 @@ __device__ __forceinline__ void rng_resolve(RngDev &rng) {
 // 4 normals for elements 4q..4q+3 of tensor `tensor`, global sample `sample`.
 __device__ __forceinline__ void philox_normal4(const RngDev &rng, uint32_t tensor, uint32_t sample,
                                                uint32_t quad, float z[4]) {
-  uint4 r = philox4x32_10(quad, sample, tensor, rng.step, rng.key0, rng.key1);
+  uint4 r = philox4x32_10(quad, sample, tensor, rng.step, rng);
   box_muller(r.x, r.y, z[0], z[1]);
   box_muller(r.z, r.w, z[2], z[3]);
 }
@@ -181,7 +188,7 @@ __device__ __forceinline__ void philox_normal4(const RngDev &rng, uint32_t tenso
 // one normal for linear element index e (slow path for rows that are not 16-byte aligned)
 __device__ __forceinline__ float philox_normal1(const RngDev &rng, uint32_t tensor, uint32_t sample,
                                                 uint64_t e) {
-  uint4 r = philox4x32_10((uint32_t)(e >> 2), sample, tensor, rng.step, rng.key0, rng.key1);
+  uint4 r = philox4x32_10((uint32_t)(e >> 2), sample, tensor, rng.step, rng);
   uint32_t lane = (uint32_t)(e & 3u);
   float z0, z1;
   if (lane < 2) box_muller(r.x, r.y, z0, z1);

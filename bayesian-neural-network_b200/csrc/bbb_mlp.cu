@@ -1,0 +1,110 @@
+// Network-level C-ABI entry points (include/bbb.h: bbb_mlp_supported / bbb_mlp_fwd / bbb_mlp_bwd): one call runs every
+// layer of a weight-sampling BBB MLP for all S Monte-Carlo samples -- the body of BayesianNetwork.sample_elbo
+// (networks.py:192-209) and of the autograd backward it triggers -- on the TMA-fed tcgen05 kernels of
+// bbb_mlp_fwd.cu / bbb_mlp_bwd.cu, with the head (last layer + likelihood + ELBO assembly) on bbb_head.cu.
+#include <mutex>
+
+#include "bbb_kernels.h"
+#include "bbb_mlp.h"
+#include "bbb_tma.cuh"
+
+using namespace bbb;
+
+namespace bbb {
+namespace tma {
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+}  // namespace tma
+}  // namespace bbb
+
+namespace {
+
+inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// the shapes the network-level kernels cover: TF32 mode, batch <= 128, every hidden width a multiple of 4, a head
+// (out <= 16) on top whose input width is a multiple of 4
+bool dims_supported(const int64_t *dims, int n_layers, int64_t S, int64_t B) {
+  if (n_layers < 2 || S < 1 || S > 65535 || B < 1 || B > 128) return false;
+  const int groups = (int)((S + 1) / 2);
+  for (int l = 0; l + 1 < n_layers; ++l) {
+    const int64_t in = dims[l], out = dims[l + 1];
+    if (in < 4 || in % 4 || out < 4 || out % 4) return false;
+    if (((out + 127) / 128) * groups > sm_count() || in * out / 4 >= ((int64_t)1 << 32)) return false;
+  }
+  const int64_t in = dims[n_layers - 1], out = dims[n_layers];
+  return out >= 1 && out <= 16 && in % 4 == 0 && in >= 4 && in <= 8192;
+}
+
+MlpLayerDesc make_desc(const bbb_mlp_layer &L, const float *x, bool x_shared) {
+  MlpLayerDesc d{};
+  d.x = x; d.x_shared = x_shared;
+  d.w_mu = L.w_mu; d.w_rho = L.w_rho; d.b_mu = L.b_mu; d.b_rho = L.b_rho; d.eps_w = L.eps_w; d.eps_b = L.eps_b;
+  d.in = L.in; d.out = L.out;
+  d.y_pre = L.y_pre; d.act = L.act; d.counters = L.counters;
+  d.dz = L.dz; d.g_w_mu = L.g_w_mu; d.g_w_rho = L.g_w_rho; d.g_b_mu = L.g_b_mu; d.g_b_rho = L.g_b_rho;
+  return d;
+}
+
+}  // namespace
+
+extern "C" int bbb_mlp_supported(const int64_t *dims, int32_t n_layers, int64_t S, int64_t B, int32_t flags) {
+  if (!dims || !(flags & BBB_F_TF32)) return 0;
+  return dims_supported(dims, n_layers, S, B) && tma::encode_fn() != nullptr ? 1 : 0;
+}
+
+extern "C" int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, int64_t S, int64_t B,
+                           const bbb_rng *rng, const bbb_prior *prior, int32_t flags, int32_t nll_kind,
+                           const void *target, float sigma, float grad_scale, float *d_out, double *logp, double *logq,
+                           double *nll, float beta, const float *beta_dev, float *out4, uint32_t *done_counter,
+                           void *stream) {
+  BBB_CHECK_ARG(layers && x && n_layers >= 2 && n_layers <= 64, "null pointer or bad layer count");
+  BBB_CHECK_ARG(flags & BBB_F_TF32, "the network-level kernels are the tcgen05 kind::tf32 path: pass BBB_F_TF32");
+  const bool sample = flags & BBB_F_SAMPLE, lpq = flags & BBB_F_LOGPROB;
+  BBB_CHECK_ARG(!lpq || (prior && logp && logq), "log-prob outputs and prior required with BBB_F_LOGPROB");
+  BBB_CHECK_ARG(!prior || prior->kind == BBB_PRIOR_GAUSSIAN || prior->kind == BBB_PRIOR_MIXTURE, "bad prior kind");
+  int64_t dims[65];
+  dims[0] = layers[0].in;
+  for (int l = 0; l < n_layers; ++l) {
+    const bbb_mlp_layer &L = layers[l];
+    BBB_CHECK_ARG(L.w_mu && L.b_mu && L.act, "null layer pointer");
+    BBB_CHECK_ARG(!(sample || lpq) || (L.w_rho && L.b_rho), "rho pointers required");
+    BBB_CHECK_ARG(!sample || (L.eps_w && L.eps_b) || (!L.eps_w && !L.eps_b && rng), "give both eps pointers or an rng");
+    BBB_CHECK_ARG(L.in == dims[l], "layer widths do not chain");
+    BBB_CHECK_ARG(l + 1 == n_layers || (L.y_pre && L.counters), "hidden layers need y_pre and counters");
+    dims[l + 1] = L.out;
+  }
+  if (!dims_supported(dims, n_layers, S, B) || !tma::encode_fn())
+    return fail(BBB_EUNSUPPORTED, "bbb_mlp_fwd: needs batch <= 128, hidden widths that are multiples of 4 and a head of at "
+                                  "most 16 outputs (see bbb_mlp_supported)");
+  cudaStream_t st = (cudaStream_t)stream;
+  PriorDev pd{};
+  if (prior) pd = make_prior_dev(prior);
+  const float *inp = x;
+  for (int l = 0; l + 1 < n_layers; ++l) {
+    bbb_rng r = rng ? *rng : bbb_rng{};
+    r.layer = (uint32_t)l;
+    MlpLayerDesc d = make_desc(layers[l], inp, l == 0);
+    if (!mlp_fwd_layer_supported(d, S, B))
+      return fail(BBB_EUNSUPPORTED, "bbb_mlp_fwd: layer %d needs 16-byte aligned tensors", l);
+    if (int rc = launch_mlp_fwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, flags | BBB_F_RELU_OUT, logp, logq, st))
+      return rc;
+    inp = layers[l].act;
+  }
+  const bbb_mlp_layer &H = layers[n_layers - 1];
+  bbb_rng r = rng ? *rng : bbb_rng{};
+  r.layer = (uint32_t)(n_layers - 1);
+  const int32_t head_flags = flags & (BBB_F_SAMPLE | BBB_F_LOGPROB);      // its input is already the activation
+  return bbb_head_fwd(inp, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b, rng ? &r : nullptr, prior, S, B,
+                      H.in, H.out, head_flags, nll_kind, target, sigma, grad_scale, H.act, d_out, logp, logq, nll, beta,
+                      beta_dev, out4, done_counter, stream);
+}

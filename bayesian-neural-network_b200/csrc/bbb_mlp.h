@@ -1,0 +1,58 @@
+// Internal interface of the network-level step for batches of at most 128 rows (bbb_mlp_fwd / bbb_mlp_bwd, include/bbb.h):
+// per-layer descriptors and the launchers of the TMA-fed tcgen05 kernels (bbb_mlp_fwd.cu, bbb_mlp_bwd.cu).
+#pragma once
+#include "bbb_common.cuh"
+
+namespace bbb {
+
+// one weight-sampling layer inside a network-level call
+struct MlpLayerDesc {
+  const float *x;            // forward input  [S,B,in], or [B,in] when x_shared (the network's input)
+  bool x_shared;
+  const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_w, *eps_b;
+  int64_t in, out;
+  float *y_pre;              // [S,B,out] zero-filled scratch: split-K partial sums of the pre-activation
+  float *act;                // [S,B,out] the layer's output (bias added, ReLU applied when BBB_F_RELU_OUT)
+  uint32_t *counters;        // zero-filled completion counters, one per (sample group, output-row tile)
+  // backward
+  const float *dz;           // [S,B,out] gradient w.r.t. the layer's pre-activation output
+  float *dx;                 // [S,B,in] zero-filled: gradient w.r.t. the PRE-activation input (masked by x > 0), or NULL
+  float *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;
+};
+
+struct MlpFwdArgs {
+  const float *b_mu, *b_rho, *eps_w, *eps_b;
+  float *y_pre, *act;
+  uint32_t *counters;
+  double *logp, *logq;
+  RngDev rng;
+  PriorDev prior;
+  int S, B, in, out, in4;
+  int n_ot, T_o, nkb;        // output-row tiles of T_o rows; 32-wide k blocks
+  int base, rem;             // CTA -> (pair, part): the first `rem` pairs get base + 1 CTAs, the others base
+  int flags, x_shared;
+};
+
+struct MlpBwdArgs {
+  const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_w, *eps_b;
+  const float *dz;           // (plain loads: bias column sums)
+  float *dx, *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;
+  RngDev rng;
+  PriorDev prior;
+  int S, B, in, out;
+  int n_ot, T_o;             // output-row tiles
+  int n_c;                   // column ranges per row tile (grid = n_c x n_ot)
+  int flags, x_shared;
+  float gp, gq;              // d loss / d logp_s, d loss / d logq_s (host factors) ...
+  const float *gp_dev, *gq_dev, *out_scale_dev;   // ... times optional device scalars (bbb_linear_bwd semantics)
+};
+
+bool mlp_fwd_layer_supported(const MlpLayerDesc &l, int64_t S, int64_t B);
+int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngDev &rng, const PriorDev &prior, int flags,
+                         double *logp, double *logq, cudaStream_t st);
+bool mlp_bwd_layer_supported(const MlpLayerDesc &l, int64_t S, int64_t B);
+int launch_mlp_bwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngDev &rng, const PriorDev &prior, int flags,
+                         float gp, float gq, const float *gp_dev, const float *gq_dev, const float *out_scale_dev,
+                         cudaStream_t st);
+
+}  // namespace bbb

@@ -1,0 +1,387 @@
+// Weight-sampling Bayesian linear layer, forward, for batches of at most 128 rows -- round-2 organisation.
+//
+//   D^T[o][b] = sum_k W_s[o][k] x_s[b][k]        (tcgen05 kind::tf32, M = 128 weight rows, N = 128 batch rows)
+//
+// The operands are swapped with respect to csrc/bbb_linear_sk.cu: the sampled weights are the A operand, so ONE
+// activation tile [128 batch rows x 32 k] serves 4096 weights (it served 1024), and it is not staged by threads at all:
+//   * warp 0 (one lane) is the TMA producer: per 32-wide k block it loads the mu and rho tiles [128 o x 32 k] (plain
+//     row layout, read back by the samplers with conflict-free 16-byte shared loads) and the activation tile(s)
+//     [128 b x 32 k] (SWIZZLE_128B = the K-major UMMA operand layout) with cp.async.bulk.tensor; out-of-range rows and
+//     columns arrive as zeros, so the kernel carries no load predicates and no address arithmetic;
+//   * warps 2..17 (512 threads) are the samplers: sigma once per weight, then per Monte-Carlo sample Philox4x32-10 ->
+//     Box-Muller -> w = mu + sigma eps, the log-prior / log-posterior terms, and one 16-byte store of the TF32-rounded
+//     quad into the SWIZZLE_128B weight tile.  Two quads x SG samples per thread and stage: straight-line code;
+//   * warp 1 (one lane) issues the MMAs and releases stages with tcgen05.commit.
+// Work split: the weight matrix is cut into (sample group, tile of T_o <= 128 output rows) pairs and every pair's k blocks
+// are divided over its share of the one-CTA-per-SM grid, so a CTA owns ONE accumulator segment.  It adds its partial
+// tile to the zero-filled pre-activation scratch with coalesced red.global.add.f32 (measured on B200: as fast as plain
+// stores, tools/b200_probe.cu) and bumps the pair's completion counter; the CTA that arrives last finalises the tile:
+// bias sample (+ its log-prob terms), optional ReLU, and a plain store of the ACTIVATION the next layer's TMA loads.
+// Hence the layer's consumers never apply ReLU or TF32 conversion while staging, which is what made the round-1 kernels
+// instruction-bound.
+#include "bbb_tc_tiles.cuh"
+#include "bbb_tma.cuh"
+#include "bbb_mlp.h"
+
+namespace bbb {
+namespace {
+
+using namespace tc;
+
+constexpr int kSamplerWarps = 16;
+constexpr int kSamplers = kSamplerWarps * 32;     // 512
+constexpr int kThreads = 64 + kSamplers;          // + TMA warp + MMA warp
+constexpr int TILE = 128 * 128;                   // bytes of one [128 rows][32 fp32] tile
+
+template <int SG>
+struct FwdCfg {
+  static constexpr int kStages = SG == 2 ? 2 : 3;
+  static constexpr int kStage = (2 + 2 * SG) * TILE;       // mu | rho | x[SG] | W[SG]
+  static constexpr int kDyn = kStages * kStage + 1024;
+  static constexpr uint32_t kTmemCols = SG * 128;
+};
+
+struct FwdCtl {
+  uint64_t full_in[3], full_w[3], empty[3], acc_full;
+  uint32_t tmem_base;
+  int is_last;
+};
+
+__device__ __forceinline__ void bar_samplers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// (no memory clobber: the __threadfence() that follows the drain orders it, and volatile asm statements keep their order)
+__device__ __forceinline__ void red_add_f32(const float *p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+// 16-byte shared-memory accesses by 32-bit shared-space address (no generic-address resolution in the inner loop)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// MODE 0: eps from Philox, 1: eps injected from memory (parity mode), 2: w = mu (no sampling)
+template <int SG, int MODE, bool kLogProb>
+__global__ void __launch_bounds__(kThreads, 1)
+ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__ CUtensorMap tm_rho,
+              const __grid_constant__ CUtensorMap tm_x, const MlpFwdArgs a) {
+  using Cfg = FwdCfg<SG>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ uint8_t dsm[];
+  __shared__ FwdCtl ctl;
+  __shared__ float bias_s[SG][128];
+  __shared__ float red[2 * SG * kSamplerWarps];
+  uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dsm) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+
+  // ---- this CTA's segment: (sample group, output-row tile) pair + a range of k blocks ---------------------------------
+  int pair, part, cnt;
+  {
+    const int bid = blockIdx.x, big = a.rem * (a.base + 1);
+    if (bid < big) { pair = bid / (a.base + 1); part = bid - pair * (a.base + 1); cnt = a.base + 1; }
+    else { const int b2 = bid - big; pair = a.rem + b2 / a.base; part = b2 - (b2 / a.base) * a.base; cnt = a.base; }
+  }
+  const int g = pair / a.n_ot, ot = pair - g * a.n_ot;
+  const int s0 = g * SG, ns = min(SG, a.S - s0);
+  const int o0 = ot * a.T_o, rows = min(a.T_o, a.out - o0);
+  const int kb0 = (int)((int64_t)part * a.nkb / cnt), kb1 = (int)((int64_t)(part + 1) * a.nkb / cnt);
+  const bool need_rho = MODE != 2 || kLogProb;
+  const int nx = a.x_shared ? 1 : ns;
+
+  if (wid == 1) tmem_alloc(smem_u32(&ctl.tmem_base), Cfg::kTmemCols);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_u32(&ctl.full_in[s]), 1);
+      mbar_init(smem_u32(&ctl.full_w[s]), kSamplerWarps);
+      mbar_init(smem_u32(&ctl.empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ctl.acc_full), 1);
+    mbar_fence_init();
+    tma::prefetch_map(&tm_mu);
+    if (need_rho) tma::prefetch_map(&tm_rho);
+    tma::prefetch_map(&tm_x);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = ctl.tmem_base;
+  pdl_wait();              // everything above is local; from here on global memory of earlier kernels is read
+
+  float lp[SG], lq[SG];
+#pragma unroll
+  for (int s = 0; s < SG; ++s) lp[s] = lq[s] = 0.0f;
+
+  if (wid == 0) {
+    // ================================ TMA producer ====================================================================
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)((1 + (need_rho ? 1 : 0) + nx) * TILE);
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int stage = it % NS;
+        if (it >= NS) mbar_wait(smem_u32(&ctl.empty[stage]), (uint32_t)(((it / NS) - 1) & 1));
+        const uint32_t sb = smem_u32(tiles + stage * Cfg::kStage), bar = smem_u32(&ctl.full_in[stage]);
+        tma::arrive_expect_tx(bar, bytes);
+        tma::load_2d(sb, &tm_mu, bar, kb * 32, o0);
+        if (need_rho) tma::load_2d(sb + TILE, &tm_rho, bar, kb * 32, o0);
+#pragma unroll
+        for (int s = 0; s < SG; ++s)
+          if (s < nx) tma::load_3d(sb + (2 + s) * TILE, &tm_x, bar, kb * 32, 0, a.x_shared ? 0 : s0 + s);
+      }
+    }
+    __syncwarp();
+    pdl_launch_dependents();
+  } else if (wid == 1) {
+    // ================================ MMA issuer ======================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, 128);
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int stage = it % NS;
+        const uint32_t ph = (uint32_t)((it / NS) & 1);
+        mbar_wait_parked(smem_u32(&ctl.full_in[stage]), ph);
+        mbar_wait_parked(smem_u32(&ctl.full_w[stage]), ph);
+        tc_fence_after_sync();
+        const uint32_t sb = smem_u32(tiles + stage * Cfg::kStage);
+#pragma unroll
+        for (int s = 0; s < SG; ++s)
+          if (s < ns)
+            tcx::issue_block(tmem + s * 128, sb + (2 + SG + s) * TILE, sb + (2 + (a.x_shared ? 0 : s)) * TILE, idesc, kb == kb0);
+        mma_commit(smem_u32(&ctl.empty[stage]));
+      }
+      mma_commit(smem_u32(&ctl.acc_full));
+    }
+    __syncwarp();
+    pdl_launch_dependents();
+  } else {
+    // ================================ samplers ========================================================================
+    RngDev rng = a.rng;
+    rng_resolve(rng);
+    const int st = tid - 64, c = st & 7, r0 = st >> 3;            // quads (row r0 + 64 j, 16-byte chunk c), j = 0, 1
+    const uint32_t w_off = sw128_off(r0, c), p_off = (uint32_t)(r0 * 128 + c * 16);
+    const bool row_ok[2] = {r0 < rows, r0 + 64 < rows};
+    const uint32_t q_base[2] = {(uint32_t)(o0 + r0) * (uint32_t)a.in4 + (uint32_t)c,
+                                (uint32_t)(o0 + r0 + 64) * (uint32_t)a.in4 + (uint32_t)c};
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    int it = 0;
+    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+      const int stage = it % NS;
+      mbar_wait(smem_u32(&ctl.full_in[stage]), (uint32_t)((it / NS) & 1));
+      const uint32_t sb = tiles_u32 + (uint32_t)(stage * Cfg::kStage);
+      const bool col_ok = kb * 32 + c * 4 < a.in;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (!row_ok[j]) {               // rows of the next tile: zero weights, so their accumulator lanes hold exact zeros
+#pragma unroll
+          for (int s = 0; s < SG; ++s)
+            if (s < ns) sts128(sb + (2 + SG + s) * TILE + w_off + j * 8192, 0.f, 0.f, 0.f, 0.f);
+          continue;
+        }
+        const float4 m4 = lds128(sb + p_off + j * 8192);
+        const float mu[4] = {m4.x, m4.y, m4.z, m4.w};
+        float sg[4] = {0.f, 0.f, 0.f, 0.f}, lsg = 0.0f;
+        if (need_rho) {
+          const float4 r4 = lds128(sb + TILE + p_off + j * 8192);
+          sg[0] = softplus_fast(r4.x); sg[1] = softplus_fast(r4.y); sg[2] = softplus_fast(r4.z); sg[3] = softplus_fast(r4.w);
+          if (kLogProb) lsg = logsigma_quad_fast(sg);
+        }
+#pragma unroll
+        for (int s = 0; s < SG; ++s) {
+          if (s >= ns) break;
+          float ep[4] = {0.f, 0.f, 0.f, 0.f}, w[4];
+          if (MODE == 0) {
+            philox_normal4(rng, rng.tensor_w, rng.sample_base + (uint32_t)(s0 + s), q_base[j] + (uint32_t)kb * 8u, ep);
+          } else if (MODE == 1) {
+            if (col_ok) {
+              const float4 e4 = __ldg(reinterpret_cast<const float4 *>(
+                  a.eps_w + ((int64_t)(s0 + s) * a.out + o0 + r0 + 64 * j) * a.in + kb * 32 + c * 4));
+              ep[0] = e4.x; ep[1] = e4.y; ep[2] = e4.z; ep[3] = e4.w;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = MODE == 2 ? mu[e] : fmaf(sg[e], ep[e], mu[e]);
+          sts128(sb + (2 + SG + s) * TILE + w_off + j * 8192, to_tf32(w[0]), to_tf32(w[1]), to_tf32(w[2]), to_tf32(w[3]));
+          if (kLogProb && col_ok) {
+            lp[s] += logp_quad_fast(a.prior, w);
+            lq[s] += -4.0f * kHalfLog2Pi - lsg - 0.5f * (ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2] + ep[3] * ep[3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(smem_u32(&ctl.full_w[stage]));
+    }
+    pdl_launch_dependents();
+
+    // ---- drain: TMEM [lane = o][column = b] -> coalesced red.add into the pre-activation scratch --------------------
+    // Accumulator lanes beyond the tile's rows and columns beyond the batch hold exact zeros (zero weight rows above,
+    // zero-filled activation rows from the TMA), so every lane adds unconditionally -- to a clamped address where its own
+    // does not exist -- and the loop carries neither predicates nor branches.
+    mbar_wait(smem_u32(&ctl.acc_full), 0u);
+    tc_fence_after_sync();
+    {
+      const int q = wid & 3, cg = (wid - 2) >> 2;          // TMEM lane quarter of this warp, 32-column group
+      const int o_l = min(q * 32 + lane, rows - 1);
+#pragma unroll
+      for (int s = 0; s < SG; ++s) {
+        if (s >= ns) break;
+        const float *yp = a.y_pre + ((int64_t)(s0 + s) * a.B) * a.out + o0 + o_l;
+#pragma unroll
+        for (int cb = 0; cb < 32; cb += 16) {
+          float v[16];
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128 + cg * 32 + cb), v);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj)
+            red_add_f32(yp + (uint32_t)min(cg * 32 + cb + jj, a.B - 1) * (uint32_t)a.out, v[jj]);
+        }
+      }
+    }
+    tc_fence_before_sync();
+    // ---- completion: the CTA that adds the last partial tile of its pair finalises it -----------------------------------
+    __threadfence();
+    bar_samplers();
+    if (st == 0) {
+      const uint32_t prev = atomicAdd(a.counters + pair, 1u);
+      ctl.is_last = prev + 1u == (uint32_t)cnt;
+    }
+    bar_samplers();
+    if (ctl.is_last) {
+      __threadfence();
+      const bool sample = MODE != 2;
+      if (st < 128 * SG) {
+        const int s = st >> 7, o_l = st & 127;
+        float bv = 0.0f;
+        if (s < ns && o_l < rows) {
+          const int o = o0 + o_l;
+          const float bmu = __ldg(a.b_mu + o);
+          const float bsg = need_rho ? softplus_f(__ldg(a.b_rho + o)) : 0.0f;
+          float ep = 0.0f;
+          if (sample)
+            ep = MODE == 1 ? __ldg(a.eps_b + (int64_t)(s0 + s) * a.out + o)
+                           : philox_normal1(rng, rng.tensor_b, rng.sample_base + (uint32_t)(s0 + s), (uint64_t)o);
+          bv = sample ? __fadd_rn(bmu, __fmul_rn(bsg, ep)) : bmu;
+          if (kLogProb) { lp[s] += logp_elem(a.prior, bv); lq[s] += logq_elem(bsg, ep); }
+        }
+        bias_s[s][o_l] = bv;
+      }
+      bar_samplers();
+      const int nq = rows >> 2, qd = st & 31;
+      const bool relu = a.flags & BBB_F_RELU_OUT;
+      if (qd < nq) {
+#pragma unroll
+        for (int s = 0; s < SG; ++s) {
+          if (s >= ns) break;
+          const float4 bq = *reinterpret_cast<const float4 *>(&bias_s[s][qd * 4]);
+          for (int b = st >> 5; b < a.B; b += 16) {
+            const int64_t off = ((int64_t)(s0 + s) * a.B + b) * a.out + o0 + qd * 4;
+            float4 v = __ldcg(reinterpret_cast<const float4 *>(a.y_pre + off));
+            v.x += bq.x; v.y += bq.y; v.z += bq.z; v.w += bq.w;
+            if (relu) v = tcx::relu4(v);
+            *reinterpret_cast<float4 *>(a.act + off) = v;
+          }
+        }
+      }
+    }
+    // ---- log-prob sums of this CTA: warp sums -> one fp64 atomic per value ---------------------------------------------
+    if (kLogProb) {
+      const int sw = wid - 2;
+#pragma unroll
+      for (int s = 0; s < SG; ++s) {
+        const float p = warp_sum(lp[s]), q2 = warp_sum(lq[s]);
+        if (lane == 0) { red[(2 * s) * kSamplerWarps + sw] = p; red[(2 * s + 1) * kSamplerWarps + sw] = q2; }
+      }
+      bar_samplers();
+      if (st < 2 * SG) {
+        const int s = st >> 1, which = st & 1;
+        if (s < ns) {
+          double v = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < kSamplerWarps; ++w8) v += (double)red[(2 * s + which) * kSamplerWarps + w8];
+          atomicAdd((which ? a.logq : a.logp) + s0 + s, v);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (wid == 1) tmem_dealloc(tmem, Cfg::kTmemCols);
+}
+
+template <int SG, int MODE, bool kLogProb>
+int launch_one(const CUtensorMap &tm_mu, const CUtensorMap &tm_rho, const CUtensorMap &tm_x, const MlpFwdArgs &a, int grid,
+               cudaStream_t st) {
+  auto kernel = ws_fwd_kernel<SG, MODE, kLogProb>;
+  BBB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<SG>::kDyn));
+  BBB_CHECK_CUDA(launch_pdl(kernel, dim3(grid), dim3(kThreads), (size_t)FwdCfg<SG>::kDyn, st, tm_mu, tm_rho, tm_x, a));
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+template <int SG>
+int launch_sg(const CUtensorMap &tm_mu, const CUtensorMap &tm_rho, const CUtensorMap &tm_x, const MlpFwdArgs &a, int grid,
+              int mode, bool lpq, cudaStream_t st) {
+  if (mode == 0) return lpq ? launch_one<SG, 0, true>(tm_mu, tm_rho, tm_x, a, grid, st) : launch_one<SG, 0, false>(tm_mu, tm_rho, tm_x, a, grid, st);
+  if (mode == 1) return lpq ? launch_one<SG, 1, true>(tm_mu, tm_rho, tm_x, a, grid, st) : launch_one<SG, 1, false>(tm_mu, tm_rho, tm_x, a, grid, st);
+  return lpq ? launch_one<SG, 2, true>(tm_mu, tm_rho, tm_x, a, grid, st) : launch_one<SG, 2, false>(tm_mu, tm_rho, tm_x, a, grid, st);
+}
+
+inline int cdiv_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+bool mlp_fwd_layer_supported(const MlpLayerDesc &l, int64_t S, int64_t B) {
+  if (!(B >= 1 && B <= 128 && S >= 1 && l.in >= 4 && l.in % 4 == 0 && l.out >= 4 && l.out % 4 == 0)) return false;
+  if (!(al16(l.x) && al16(l.w_mu) && al16(l.w_rho) && al16(l.eps_w) && al16(l.y_pre) && al16(l.act))) return false;
+  const int n_ot = cdiv_i(l.out, 128), groups = cdiv_i(S, 2);
+  return (int64_t)n_ot * groups <= sm_count() && l.in * l.out / 4 < (int64_t)1 << 32;
+}
+
+// One layer: x [Sx,B,in] (x_shared: [B,in]) -> act [S,B,out] = (relu)(x W_s^T + b_s), log-prob sums added to logp/logq.
+// y_pre [S,B,out] and counters [groups * n_ot] must be zero-filled.
+int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngDev &rng, const PriorDev &prior, int flags,
+                         double *logp, double *logq, cudaStream_t st) {
+  const bool sample = flags & BBB_F_SAMPLE, lpq = flags & BBB_F_LOGPROB;
+  const int mode = !sample ? 2 : (l.eps_w ? 1 : 0);
+  MlpFwdArgs a{};
+  a.b_mu = l.b_mu; a.b_rho = l.b_rho; a.eps_w = l.eps_w; a.eps_b = l.eps_b;
+  a.y_pre = l.y_pre; a.act = l.act; a.counters = l.counters; a.logp = logp; a.logq = logq;
+  a.rng = rng; a.prior = prior;
+  a.S = (int)S; a.B = (int)B; a.in = (int)l.in; a.out = (int)l.out; a.in4 = (int)(l.in / 4);
+  a.n_ot = cdiv_i(l.out, 128);
+  a.T_o = ((cdiv_i(l.out, a.n_ot) + 3) / 4) * 4;
+  a.n_ot = cdiv_i(l.out, a.T_o);
+  a.nkb = cdiv_i(l.in, 32);
+  a.flags = flags; a.x_shared = l.x_shared ? 1 : 0;
+  const int sg = S >= 2 ? 2 : 1, groups = cdiv_i(S, sg), pairs = groups * a.n_ot;
+  int grid = sm_count();
+  if ((int64_t)pairs * a.nkb < grid) grid = pairs * a.nkb;
+  a.base = grid / pairs; a.rem = grid % pairs;
+  CUtensorMap tm_mu, tm_rho, tm_x;
+  if (int r = tma::make_map(&tm_mu, l.w_mu, l.in, l.out, 0, 32, 128, tma::kNone)) return r;
+  tm_rho = tm_mu;
+  if (l.w_rho)
+    if (int r = tma::make_map(&tm_rho, l.w_rho, l.in, l.out, 0, 32, 128, tma::kNone)) return r;
+  if (int r = tma::make_map(&tm_x, l.x, l.in, B, l.x_shared ? 1 : S, 32, 128, tma::kSw128)) return r;
+  return sg == 2 ? launch_sg<2>(tm_mu, tm_rho, tm_x, a, grid, mode, lpq, st) : launch_sg<1>(tm_mu, tm_rho, tm_x, a, grid, mode, lpq, st);
+}
+
+}  // namespace bbb

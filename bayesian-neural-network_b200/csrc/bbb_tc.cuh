@@ -143,12 +143,10 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
   return (uint32_t)(((row >> 3) << 10) + ((row & 7) << 7) + ((chunk ^ (row & 7)) << 4));
 }
-// fp32 -> tf32 with round-to-nearest (the tensor core itself would truncate the low 13 mantissa bits)
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+// fp32 -> tf32 with round-to-nearest (ties away, as cvt.rna.tf32.f32): the tensor core itself truncates the low 13
+// mantissa bits of whatever it reads, so adding half a TF32 ulp to the bit pattern is the whole conversion -- one
+// integer add where cvt.rna compiles to four instructions
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ void st_tile4(uint8_t *tile, int row, int chunk, float a, float b, float c, float d) {
   *reinterpret_cast<float4 *>(tile + sw128_off(row, chunk)) = make_float4(to_tf32(a), to_tf32(b), to_tf32(c), to_tf32(d));
 }

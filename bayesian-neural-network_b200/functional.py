@@ -370,6 +370,104 @@ def mlp_forward(x2, layers, prior, S, sample=True, logprob=True, tf32=False):
     return _MLPForward.apply(x2, prior, S, sample, logprob, tf32, *flat)
 
 
+def _layerwise_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, tf32, beta_h, beta_d, out4):
+    """sample_elbo's forward as one launch per layer (+ the fused head): every shape, both modes.  Returns
+    (ys: per-layer PRE-activation outputs, dxs: the backward's zero-filled dx workspace, d_out)."""
+    dev = x2.device
+    # ONE zero-filled workspace (one memset per step): fp64 accumulators + the head's completion counter |
+    # activations of every layer | dx of every layer above the first (the backward's split-K kernels add into them)
+    shapes = [(2 * (2 * S + 1) + 2,)] + [(S, B, p[0].shape[0]) for p in params]
+    if need_grad:
+        shapes += [(S, B, p[0].shape[1]) for p in params[1:]]
+    if _prezero(B):
+        ws = _zeroed_views(shapes, dev)
+    else:                      # large batch: only the accumulators are zeroed
+        ws = _zeroed_views(shapes[:1], dev) + _workspace(shapes[1:], dev, False)
+    acc = ws[0][:2 * (2 * S + 1)].view(torch.float64)
+    done = ws[0][2 * (2 * S + 1):]
+    ys, dxs = ws[1:1 + len(params)], ([None] + ws[1 + len(params):] if need_grad else None)
+    logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
+    Cc = params[-1][0].shape[0]
+    d_out = torch.empty((S, B, Cc), dtype=torch.float32, device=dev) if need_grad else None
+    if head_eligible(params[-1]):
+        # the last layer, the likelihood with its gradient and the assembly of the four scalars: one launch
+        tgt = target if mode == 'classification' else _f32c(target)
+        nl = len(params) - 1
+
+        def head(inp, stride, flags, y):
+            _ws_head(inp, stride, params[nl], eps, nl, prior, S, B, flags, y, logp, logq, mode, tgt, sigma, d_out,
+                     nll, beta_h, beta_d, out4, done)
+        ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq, ys, head)
+    else:
+        ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq, ys)
+        out = ys[-1]
+        if mode == 'classification':
+            L.check(L.lib().bbb_nll_ce(L.ptr(out), L.ptr(target), S, B, Cc, 1.0 / S, L.ptr(nll), L.ptr(d_out),
+                                       L.stream()), 'bbb_nll_ce')
+        else:
+            tgt = _f32c(target)
+            L.check(L.lib().bbb_nll_gauss(L.ptr(out), L.ptr(tgt), float(sigma), S, B, Cc, 1.0 / S, L.ptr(nll),
+                                          L.ptr(d_out), L.stream()), 'bbb_nll_gauss')
+        L.check(L.lib().bbb_elbo_finalize(L.ptr(logp), L.ptr(logq), None, L.ptr(nll), S, beta_h, L.ptr(beta_d),
+                                          L.ptr(out4), L.stream()), 'bbb_elbo_finalize')
+    return ys, dxs, d_out
+
+
+def _mlp_layer_table(params, eps, ypre, acts, counters, dzs, grads):
+    tab = (L.MlpLayer * len(params))()
+    for l, p in enumerate(params):
+        t = tab[l]
+        t.w_mu, t.w_rho, t.b_mu, t.b_rho = (q.data_ptr() for q in p)
+        t.eps_w, t.eps_b = eps.ptrs(l)
+        t.out, t.inn = p[0].shape
+        t.y_pre, t.act = L.ptr(ypre[l]), L.ptr(acts[l])
+        t.counters, t.dz = L.ptr(counters[l]), L.ptr(dzs[l])
+        if grads is not None:
+            t.g_w_mu, t.g_w_rho, t.g_b_mu, t.g_b_rho = (g.data_ptr() for g in grads[l])
+    return tab
+
+
+def _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, beta_h, beta_d, out4):
+    """sample_elbo's forward as ONE C call (bbb_mlp_fwd): TMA-fed tcgen05 kernels for the hidden layers, whose outputs
+    are stored as ACTIVATIONS (post-ReLU), + the fused head.  Returns (acts, dxs, d_out) with acts[l] the post-ReLU
+    output of hidden layer l (max(., 0) is idempotent and (relu(y) > 0) == (y > 0), so the backward can take them where
+    it took the pre-activations) and dxs[l] the zero-filled gradient buffer w.r.t. layer l's pre-activation input."""
+    dev = x2.device
+    nl = len(params)
+    groups = (S + 1) // 2
+    hidden = [p[0].shape[0] for p in params[:-1]]
+    n_cnt = [groups * ((h + 127) // 128) for h in hidden]
+    # zero-filled (one memset): fp64 accumulators, done counter, tile counters | split-K scratch of every hidden layer |
+    # gradient w.r.t. every hidden layer's pre-activation output (the layer above adds its partial dx tiles into it)
+    shapes = [(2 * (2 * S + 1) + 2 + sum(n_cnt),)] + [(S, B, h) for h in hidden]
+    if need_grad:
+        shapes += [(S, B, h) for h in hidden]
+    ws = _zeroed_views(shapes, dev)
+    head = ws[0]
+    acc = head[:2 * (2 * S + 1)].view(torch.float64)
+    done = head[2 * (2 * S + 1):2 * (2 * S + 1) + 2]
+    counters, off = [], 2 * (2 * S + 1) + 2
+    for n in n_cnt:
+        counters.append(head[off:off + n])
+        off += n
+    counters.append(None)
+    ypre = ws[1:1 + len(hidden)] + [None]
+    dzs = (ws[1 + len(hidden):] if need_grad else [None] * len(hidden))
+    logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
+    acts = [torch.empty((S, B, p[0].shape[0]), dtype=torch.float32, device=dev) for p in params]
+    Cc = params[-1][0].shape[0]
+    d_out = torch.empty((S, B, Cc), dtype=torch.float32, device=dev) if need_grad else None
+    tab = _mlp_layer_table(params, eps, ypre, acts, counters, list(dzs) + [d_out], None)
+    kind = L.NLL_CE if mode == 'classification' else L.NLL_GAUSS
+    tgt = target if mode == 'classification' else _f32c(target)
+    rng = eps.rng(0)
+    L.check(L.lib().bbb_mlp_fwd(tab, nl, L.ptr(x2), S, B, C.byref(rng), C.byref(prior),
+                                L.F_SAMPLE | L.F_LOGPROB | L.F_TF32, kind, L.ptr(tgt), float(sigma), 1.0 / S,
+                                L.ptr(d_out), L.ptr(logp), L.ptr(logq), L.ptr(nll), beta_h, L.ptr(beta_d), L.ptr(out4),
+                                L.ptr(done), L.stream()), 'bbb_mlp_fwd')
+    return acts, ([None] + list(dzs) if need_grad else None), d_out
+
+
 class _FusedELBO(torch.autograd.Function):
     """sample_elbo (networks.py:192-209) as 3 forward launches + likelihood + assembly; the
     backward is 5 launches.  Only `loss` is differentiable."""
@@ -383,44 +481,18 @@ class _FusedELBO(torch.autograd.Function):
         eps = plan_eps([(tuple(p[0].shape), (p[0].shape[0],)) for p in params], S, dev, True)
         need_grad = any(t.requires_grad for t in flat)
         B = x2.shape[0]
-        # ONE zero-filled workspace (one memset per step): fp64 accumulators + the head's completion counter |
-        # activations of every layer | dx of every layer above the first (the backward's split-K kernels add into them)
-        shapes = [(2 * (2 * S + 1) + 2,)] + [(S, B, p[0].shape[0]) for p in params]
-        if need_grad:
-            shapes += [(S, B, p[0].shape[1]) for p in params[1:]]
-        if _prezero(B):
-            ws = _zeroed_views(shapes, dev)
-        else:                      # large batch: only the accumulators are zeroed
-            ws = _zeroed_views(shapes[:1], dev) + _workspace(shapes[1:], dev, False)
-        acc = ws[0][:2 * (2 * S + 1)].view(torch.float64)
-        done = ws[0][2 * (2 * S + 1):]
-        ys, dxs = ws[1:1 + len(params)], ([None] + ws[1 + len(params):] if need_grad else None)
-        logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
         Cc = params[-1][0].shape[0]
-        d_out = torch.empty((S, B, Cc), dtype=torch.float32, device=dev) if need_grad else None
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
         beta_h, beta_d = _split_beta(beta)
-        if head_eligible(params[-1]):
-            # the last layer, the likelihood with its gradient and the assembly of the four scalars: one launch
-            tgt = target if mode == 'classification' else _f32c(target)
-            nl = len(params) - 1
-
-            def head(inp, stride, flags, y):
-                _ws_head(inp, stride, params[nl], eps, nl, prior, S, B, flags, y, logp, logq, mode, tgt, sigma, d_out,
-                         nll, beta_h, beta_d, out4, done)
-            ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq, ys, head)
+        dims = [params[0][0].shape[1]] + [p[0].shape[0] for p in params]
+        use_mlp = (tf32 and fused_opt is None and mode in ('classification', 'regression') and
+                   L.mlp_supported(dims, S, B, L.F_TF32))
+        if use_mlp:
+            ys, dxs, d_out = _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, beta_h,
+                                               beta_d, out4)
         else:
-            ys = _net_ws_forward(x2, params, prior, S, eps, True, True, tf32, logp, logq, ys)
-            out = ys[-1]
-            if mode == 'classification':
-                L.check(L.lib().bbb_nll_ce(L.ptr(out), L.ptr(target), S, B, Cc, 1.0 / S, L.ptr(nll), L.ptr(d_out),
-                                           L.stream()), 'bbb_nll_ce')
-            else:
-                tgt = _f32c(target)
-                L.check(L.lib().bbb_nll_gauss(L.ptr(out), L.ptr(tgt), float(sigma), S, B, Cc, 1.0 / S, L.ptr(nll),
-                                              L.ptr(d_out), L.stream()), 'bbb_nll_gauss')
-            L.check(L.lib().bbb_elbo_finalize(L.ptr(logp), L.ptr(logq), None, L.ptr(nll), S, beta_h, L.ptr(beta_d),
-                                              L.ptr(out4), L.stream()), 'bbb_elbo_finalize')
+            ys, dxs, d_out = _layerwise_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, tf32,
+                                                     beta_h, beta_d, out4)
         if need_grad:
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *eps.tensors())
             ctx.dxs = dxs

@@ -53,6 +53,7 @@ extern "C" {
 #define BBB_F_NO_WGRAD 128 /* backward: do not compute parameter gradients (dx only)           */
 #define BBB_F_DX_PREACT 512 /* backward, with BBB_F_RELU_IN: dx is multiplied by (x > 0), i.e. it is the gradient
                               w.r.t. the PRE-activation input; the layer below then needs no dy_mask_src      */
+#define BBB_F_RELU_OUT 1024 /* network-level forward (bbb_mlp_fwd): the layer stores max(y, 0), the ACTIVATION its consumer loads */
 #define BBB_F_OUT_ZEROED 256 /* y (forward) / dx (backward) is already zero-filled by the caller: kernels that
                                combine split-K partial sums with red.add skip their own memset              */
 
@@ -199,6 +200,38 @@ int bbb_head_fwd(const float *x, int64_t x_sample_stride, const float *w_mu, con
                  int32_t flags, int32_t nll_kind, const void *target, float sigma, float grad_scale,
                  float *y, float *dy, double *logp, double *logq, double *nll, float beta,
                  const float *beta_dev, float *out4, uint32_t *done_counter, void *stream);
+
+/* ---- the whole network in one call (batches of at most 128 rows, tcgen05 kind::tf32) ---------------------------------
+ * bbb_mlp_fwd = the body of BayesianNetwork.sample_elbo (networks.py:192-209): BayesianNetwork.forward (166-172) for
+ * all S samples -- every hidden BayesianLinear.forward (73-88) followed by ReLU -- then the head as bbb_head_fwd does
+ * it (last layer + get_nll (183-190) and its gradient + the four returned scalars).  Replaces n_layers calls of
+ * bbb_linear_fwd / bbb_head_fwd: one host call per network pass, and a different data flow between the layers: a
+ * hidden layer's output is stored as the ACTIVATION max(x W_s^T + b_s, 0) (its split-K partial tiles are added into
+ * the zero-filled y_pre scratch and the CTA that completes a tile finalises it), so that the next layer -- and the
+ * backward -- load it with TMA exactly as it lies.
+ *   layers[l]  w_mu, w_rho [out,in]; b_mu, b_rho [out]; eps_w [S,out,in] / eps_b [S,out] or NULL (Philox, tensor ids
+ *              2l / 2l+1: rng->layer is ignored);  in of layer l+1 == out of layer l
+ *              y_pre [S,B,out] zero-filled scratch and counters (cdiv(S,2) * cdiv(out,128) zero-filled words): hidden layers
+ *              act   [S,B,out] written: hidden layers the activation, last layer the network's outputs
+ *              dz, g_*: backward only (bbb_mlp_bwd)
+ *   x [B,in0] is shared by all samples;  nll_kind / target / sigma / grad_scale / d_out / nll / beta / beta_dev / out4 /
+ *   done_counter exactly as in bbb_head_fwd (d_out [S,B,out_last] = grad_scale * d nll / d outputs).
+ * bbb_mlp_supported: 1 when bbb_mlp_fwd / bbb_mlp_bwd cover this network (dims[0..n_layers], BBB_F_TF32 in flags, B <= 128,
+ * hidden widths multiples of 4, last layer a head of <= 16 outputs), else 0; otherwise the calls return
+ * BBB_EUNSUPPORTED without launching anything and the per-layer entry points apply. */
+typedef struct bbb_mlp_layer {
+  const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_w, *eps_b;
+  int64_t in, out;
+  float *y_pre, *act;
+  uint32_t *counters;
+  float *dz;                                      /* [S,B,out]: hidden layers zero-filled, accumulated by the layer above */
+  float *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;     /* parameter gradients, overwritten                                     */
+} bbb_mlp_layer;
+int bbb_mlp_supported(const int64_t *dims, int32_t n_layers, int64_t S, int64_t B, int32_t flags);
+int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, int64_t S, int64_t B,
+                const bbb_rng *rng, const bbb_prior *prior, int32_t flags, int32_t nll_kind, const void *target,
+                float sigma, float grad_scale, float *d_out, double *logp, double *logq, double *nll, float beta,
+                const float *beta_dev, float *out4, uint32_t *done_counter, void *stream);
 
 /* ELBO assembly (networks.py:205-209 / 221-225):
  * out4 = { beta mean(logq) - beta mean(logp) + nll/S, mean(logp), mean(logq), nll/S }   (kl == NULL)

@@ -14,7 +14,7 @@ import numpy as np
 from oracle import closed_form as CF
 
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
-F_OUT_ZEROED, F_DX_PREACT = 256, 512
+F_OUT_ZEROED, F_DX_PREACT, F_RELU_OUT = 256, 512, 1024
 
 
 def _arr(ptr, ctype, *shape):
@@ -283,6 +283,38 @@ class FakeLib:
         if out4:
             assert done and _arr(done, C.c_uint32, 1)[0] == 0, 'fake lib: done counter must be zeroed'
             self.bbb_elbo_finalize(logp, logq, None, nll, S, beta, beta_dev, out4, st)
+        return 0
+
+    # ---------------------------------------------------------------- the whole network in one call
+    def bbb_mlp_supported(self, dims, n_layers, S, B, flags):
+        d = list(dims)
+        if not (flags & F_TF32) or n_layers < 2 or not (1 <= B <= 128) or S < 1:
+            return 0
+        hidden_ok = all(d[l] >= 4 and d[l] % 4 == 0 and d[l + 1] >= 4 and d[l + 1] % 4 == 0 for l in range(n_layers - 1))
+        return int(hidden_ok and 1 <= d[n_layers] <= 16 and d[n_layers - 1] % 4 == 0 and 4 <= d[n_layers - 1] <= 8192)
+
+    def bbb_mlp_fwd(self, layers, n_layers, x, S, B, rng, prior, flags, nll_kind, target, sigma, scale, d_out, logp, logq,
+                    nll, beta, beta_dev, out4, done, st):
+        """hidden layers: act = relu(x W_s^T + b_s) (y_pre / counters are kernel scratch and must arrive zeroed);
+        last layer: bbb_head_fwd on the last activation"""
+        self.calls.append('mlp_fwd')
+        n0 = len(self.calls)
+        inp, xs = x, 0
+        for l in range(n_layers - 1):
+            t = layers[l]
+            assert t.y_pre and t.counters and t.act, 'fake lib: hidden layers need y_pre, counters and act'
+            assert not np.any(_f(t.y_pre, S, B, t.out)) and _arr(t.counters, C.c_uint32, 1)[0] == 0, 'scratch must be zeroed'
+            self.bbb_linear_fwd(inp, xs, t.w_mu, t.w_rho, t.b_mu, t.b_rho, t.eps_w, t.eps_b, rng, prior, S, B, t.inn,
+                                t.out, flags & (F_SAMPLE | F_LOGPROB), t.act, logp, logq, st)
+            A = _f(t.act, S, B, t.out)
+            A[...] = np.maximum(A, 0)
+            inp, xs = t.act, B * t.out
+        t = layers[n_layers - 1]
+        self.bbb_head_fwd(inp, xs, t.w_mu, t.w_rho, t.b_mu, t.b_rho, t.eps_w, t.eps_b, rng, prior, S, B, t.inn, t.out,
+                          flags & (F_SAMPLE | F_LOGPROB), nll_kind, target, sigma, scale, t.act, d_out, logp, logq, nll,
+                          beta, beta_dev, out4, done, st)
+        del self.calls[n0:]
+        self.calls.append('head_fwd')
         return 0
 
     def bbb_elbo_finalize(self, logp, logq, kl, nll, S, beta, beta_dev, out4, st):

@@ -30,6 +30,17 @@ def test_train_step_network_level(fake, name, fused):
     assert fused_used == expect_fused        # [B] vs [B,1] broadcast targets (SURVEY B-3) take the general path
 
 
+@pytest.mark.parametrize('name', ['small_cls_mix', 'small_cls_gauss', 'deep5_small_mix'])
+def test_train_step_through_the_network_level_call(fake, name):
+    """tf32=True routes sample_elbo through ONE bbb_mlp_fwd call when bbb_mlp_supported says so (hidden widths that are
+    multiples of 4, a head on top), otherwise through the per-layer calls; same results either way."""
+    case = Case(name)
+    PC.check_train_step(case, 'cpu', fused=True, tf32=True)
+    expect = all(d % 4 == 0 for d in case.dims[:-1])
+    assert ('mlp_fwd' in fake.calls) == expect
+    assert ('linear_fwd' in fake.calls) == (not expect)
+
+
 @pytest.mark.parametrize('name', SMALL + SMALL_LR)
 def test_train_step_layer_level(fake, name):
     PC.check_layerwise_train_step(Case(name), 'cpu')
