@@ -108,3 +108,55 @@ extern "C" int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
                       H.in, H.out, head_flags, nll_kind, target, sigma, grad_scale, H.act, d_out, logp, logq, nll, beta,
                       beta_dev, out4, done_counter, stream);
 }
+
+extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, int64_t S, int64_t B,
+                           const bbb_rng *rng, const bbb_prior *prior, int32_t flags, float gp, float gq,
+                           const float *gp_dev, const float *gq_dev, int64_t g_dev_stride, const float *out_scale_dev,
+                           void *stream) {
+  BBB_CHECK_ARG(layers && x && n_layers >= 2 && n_layers <= 64, "null pointer or bad layer count");
+  BBB_CHECK_ARG(flags & BBB_F_TF32, "the network-level kernels are the tcgen05 kind::tf32 path: pass BBB_F_TF32");
+  BBB_CHECK_ARG(g_dev_stride == 0 || g_dev_stride == 1, "g_dev_stride must be 0 or 1");
+  BBB_CHECK_ARG(((gp == 0.0f) && !gp_dev) || prior, "prior required when gp != 0");
+  const bool sample = flags & BBB_F_SAMPLE;
+  int64_t dims[65];
+  dims[0] = layers[0].in;
+  for (int l = 0; l < n_layers; ++l) {
+    const bbb_mlp_layer &L = layers[l];
+    BBB_CHECK_ARG(L.w_mu && L.w_rho && L.b_mu && L.b_rho && L.dz && L.g_w_mu && L.g_w_rho && L.g_b_mu && L.g_b_rho,
+                  "null layer pointer");
+    BBB_CHECK_ARG(!sample || (L.eps_w && L.eps_b) || (!L.eps_w && !L.eps_b && rng), "give both eps pointers or an rng");
+    BBB_CHECK_ARG(L.in == dims[l], "layer widths do not chain");
+    BBB_CHECK_ARG(l + 1 == n_layers || L.act, "hidden layers need their stored activation");
+    dims[l + 1] = L.out;
+  }
+  if (!dims_supported(dims, n_layers, S, B) || !tma::encode_fn())
+    return fail(BBB_EUNSUPPORTED, "bbb_mlp_bwd: needs batch <= 128, hidden widths that are multiples of 4 and a head of at "
+                                  "most 16 outputs (see bbb_mlp_supported)");
+  cudaStream_t st = (cudaStream_t)stream;
+  PriorDev pd{};
+  if (prior) pd = make_prior_dev(prior);
+  const int32_t keep = flags & (BBB_F_SAMPLE | BBB_F_TF32 | BBB_F_ACCUM);
+  // the head: dz of the last hidden layer = (d_out W_s) (act > 0), added into its zero-filled buffer
+  {
+    const bbb_mlp_layer &H = layers[n_layers - 1], &P = layers[n_layers - 2];
+    bbb_rng r = rng ? *rng : bbb_rng{};
+    r.layer = (uint32_t)(n_layers - 1);
+    if (int rc = bbb_linear_bwd(H.dz, nullptr, P.act, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b,
+                                rng ? &r : nullptr, prior, S, B, H.in, H.out,
+                                keep | BBB_F_RELU_IN | BBB_F_DX_PREACT | BBB_F_OUT_ZEROED, gp, gq, gp_dev, gq_dev,
+                                g_dev_stride, out_scale_dev, P.dz, H.g_w_mu, H.g_w_rho, H.g_b_mu, H.g_b_rho, stream))
+      return rc;
+  }
+  for (int l = n_layers - 2; l >= 0; --l) {
+    bbb_rng r = rng ? *rng : bbb_rng{};
+    r.layer = (uint32_t)l;
+    MlpLayerDesc d = make_desc(layers[l], l > 0 ? layers[l - 1].act : x, l == 0);
+    d.dx = l > 0 ? layers[l - 1].dz : nullptr;
+    if (!mlp_bwd_layer_supported(d, S, B))
+      return fail(BBB_EUNSUPPORTED, "bbb_mlp_bwd: layer %d needs 16-byte aligned tensors", l);
+    if (int rc = launch_mlp_bwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, keep, gp, gq, gp_dev, gq_dev,
+                                      (int)g_dev_stride, out_scale_dev, st))
+      return rc;
+  }
+  return BBB_OK;
+}

@@ -36,6 +36,7 @@ struct MlpFwdArgs {
 struct MlpBwdArgs {
   const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_w, *eps_b;
   const float *dz;           // (plain loads: bias column sums)
+  const float *x;            // (plain loads: the (x > 0) mask of dgrad)
   float *dx, *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;
   RngDev rng;
   PriorDev prior;
@@ -45,6 +46,7 @@ struct MlpBwdArgs {
   int flags, x_shared;
   float gp, gq;              // d loss / d logp_s, d loss / d logq_s (host factors) ...
   const float *gp_dev, *gq_dev, *out_scale_dev;   // ... times optional device scalars (bbb_linear_bwd semantics)
+  int g_dev_stride;
 };
 
 bool mlp_fwd_layer_supported(const MlpLayerDesc &l, int64_t S, int64_t B);
@@ -52,7 +54,7 @@ int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngD
                          double *logp, double *logq, cudaStream_t st);
 bool mlp_bwd_layer_supported(const MlpLayerDesc &l, int64_t S, int64_t B);
 int launch_mlp_bwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngDev &rng, const PriorDev &prior, int flags,
-                         float gp, float gq, const float *gp_dev, const float *gq_dev, const float *out_scale_dev,
-                         cudaStream_t st);
+                         float gp, float gq, const float *gp_dev, const float *gq_dev, int g_dev_stride,
+                         const float *out_scale_dev, cudaStream_t st);
 
 }  // namespace bbb

@@ -370,6 +370,11 @@ def mlp_forward(x2, layers, prior, S, sample=True, logprob=True, tf32=False):
     return _MLPForward.apply(x2, prior, S, sample, logprob, tf32, *flat)
 
 
+# sample_elbo in TF32 mode goes through ONE C call per network pass (bbb_mlp_fwd / bbb_mlp_bwd) when the library covers
+# the network (bbb_mlp_supported); False forces the per-layer calls (A/B measurements, tools/check_mlp.py)
+use_network_level_call = True
+
+
 def _layerwise_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, tf32, beta_h, beta_d, out4):
     """sample_elbo's forward as one launch per layer (+ the fused head): every shape, both modes.  Returns
     (ys: per-layer PRE-activation outputs, dxs: the backward's zero-filled dx workspace, d_out)."""
@@ -485,7 +490,7 @@ class _FusedELBO(torch.autograd.Function):
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
         beta_h, beta_d = _split_beta(beta)
         dims = [params[0][0].shape[1]] + [p[0].shape[0] for p in params]
-        use_mlp = (tf32 and fused_opt is None and mode in ('classification', 'regression') and
+        use_mlp = (use_network_level_call and tf32 and mode in ('classification', 'regression') and
                    L.mlp_supported(dims, S, B, L.F_TF32))
         if use_mlp:
             ys, dxs, d_out = _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, beta_h,
@@ -496,6 +501,7 @@ class _FusedELBO(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(x2, d_out, *flat, *ys[:-1], *eps.tensors())
             ctx.dxs = dxs
+        ctx.used_mlp = use_mlp
         ctx.cfg = (prior, S, beta_h, tf32, eps, len(params))
         ctx.beta_dev = beta_d
         ctx.set_materialize_grads(False)      # no zero-filled gradients for the three non-differentiable scalars
@@ -525,8 +531,23 @@ class _FusedELBO(torch.autograd.Function):
                 _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S, bd, bd, 0,
                                  scale, False, ctx.fused_opt, ctx.live, ctx.dxs)
             return (None,) * (9 + 4 * nl)
-        _, grads = _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S,
-                                    bd, bd, 0, scale, False, dxs=ctx.dxs)
+        if ctx.used_mlp:
+            # ONE C call for the whole backward (bbb_mlp_bwd): ys are the stored activations, ctx.dxs[l + 1] the
+            # zero-filled gradient w.r.t. hidden layer l's pre-activation output
+            grads = _alloc_grads(params)
+            B = x2.shape[0]
+            dzs = list(ctx.dxs[1:]) + [d_out]
+            tab = _mlp_layer_table(params, eps, [None] * nl, ys, [None] * nl, dzs, grads)
+            rng = eps.rng(0)
+            L.check(L.lib().bbb_mlp_bwd(tab, nl, L.ptr(x2), S, B, C.byref(rng), C.byref(prior), L.F_SAMPLE | L.F_TF32,
+                                        -beta / S, beta / S, L.ptr(bd), L.ptr(bd), 0, L.ptr(scale), L.stream()),
+                    'bbb_mlp_bwd')
+            if grad_ready_hook is not None:
+                for l in reversed(range(nl)):
+                    grad_ready_hook(l, grads[l].flat)
+        else:
+            _, grads = _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S,
+                                        bd, bd, 0, scale, False, dxs=ctx.dxs)
         flat = [g for lg in grads for g in lg]
         return (None,) * 9 + tuple(flat)
 

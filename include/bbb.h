@@ -232,6 +232,15 @@ int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, i
                 const bbb_rng *rng, const bbb_prior *prior, int32_t flags, int32_t nll_kind, const void *target,
                 float sigma, float grad_scale, float *d_out, double *logp, double *logq, double *nll, float beta,
                 const float *beta_dev, float *out4, uint32_t *done_counter, void *stream);
+/* bbb_mlp_bwd = the autograd backward of the above (triggered at reg_task.py:72, class_task.py:78, bandits.py:49), all
+ * layers in one call; replaces n_layers calls of bbb_linear_bwd (same gp / gq / gp_dev / gq_dev / g_dev_stride /
+ * out_scale_dev meaning, eps regenerated from the same Philox coordinates).  Reads layers[l].act (the activations the
+ * forward stored) and layers[n-1].dz (= d_out of bbb_mlp_fwd); layers[l].dz of the hidden layers must be zero-filled:
+ * the layer above adds (dz W_s) (act > 0) into it.  Writes g_w_mu / g_w_rho / g_b_mu / g_b_rho of every layer
+ * (added to with BBB_F_ACCUM). */
+int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, int64_t S, int64_t B,
+                const bbb_rng *rng, const bbb_prior *prior, int32_t flags, float gp, float gq, const float *gp_dev,
+                const float *gq_dev, int64_t g_dev_stride, const float *out_scale_dev, void *stream);
 
 /* ELBO assembly (networks.py:205-209 / 221-225):
  * out4 = { beta mean(logq) - beta mean(logp) + nll/S, mean(logp), mean(logq), nll/S }   (kl == NULL)

@@ -317,6 +317,25 @@ class FakeLib:
         self.calls.append('head_fwd')
         return 0
 
+    def bbb_mlp_bwd(self, layers, n_layers, x, S, B, rng, prior, flags, gp, gq, gp_dev, gq_dev, gstride, oscale, st):
+        """backward of bbb_mlp_fwd: per layer bbb_linear_bwd on the stored activations; the gradient w.r.t. a hidden
+        layer's pre-activation output is ADDED into its (zero-filled) dz buffer"""
+        self.calls.append('mlp_bwd')
+        n0 = len(self.calls)
+        for l in reversed(range(n_layers)):
+            t = layers[l]
+            inp, xs = (layers[l - 1].act, B * t.inn) if l > 0 else (x, 0)
+            fl = (flags & (F_SAMPLE | F_ACCUM)) | ((F_RELU_IN | F_DX_PREACT) if l > 0 else F_NO_DX)
+            dx = None
+            if l > 0:
+                assert not np.any(_f(layers[l - 1].dz, S, B, t.inn)), 'fake lib: hidden dz buffers must be zeroed'
+                dx = layers[l - 1].dz
+            self.bbb_linear_bwd(t.dz, None, inp, xs, t.w_mu, t.w_rho, t.b_mu, t.b_rho, t.eps_w, t.eps_b, rng, prior, S, B,
+                                t.inn, t.out, fl, gp, gq, gp_dev, gq_dev, gstride, oscale, dx, t.g_w_mu, t.g_w_rho,
+                                t.g_b_mu, t.g_b_rho, st)
+        del self.calls[n0:]
+        return 0
+
     def bbb_elbo_finalize(self, logp, logq, kl, nll, S, beta, beta_dev, out4, st):
         O = _f(out4, 4)
         if beta_dev:

@@ -41,6 +41,9 @@ def run(dims, B, S, mode, tf32, seed=3):
 
 def main():
     cases = CASES[:2] if '--quick' in sys.argv else CASES
+    if '--layerwise' in sys.argv:        # the per-layer TF32 kernels against the exact path: the baseline of this check
+        from bnn_b200 import functional as F
+        F.use_network_level_call = False
     ok = True
     for dims, B, S, mode in cases:
         t0 = time.time()
