@@ -74,6 +74,8 @@ _SIGS = {
     'bbb_ipc_open': ([C.c_char_p, I64, P], C.c_int),
     'bbb_adam_step_peer': ([P, P, P, I64, F64, F64, F64, F64, U32, P, P, P], C.c_int),
     'bbb_counter_add': ([P, U32, P], C.c_int),
+    'bbb_timing_enable': ([I32], C.c_int),
+    'bbb_timing_report': ([C.c_char_p, I64], C.c_int),
 }
 EXPORTS = tuple(_SIGS)
 

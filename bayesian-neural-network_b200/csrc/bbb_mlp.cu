@@ -3,6 +3,9 @@
 // (networks.py:192-209) and of the autograd backward it triggers -- on the TMA-fed tcgen05 kernels of
 // bbb_mlp_fwd.cu / bbb_mlp_bwd.cu, with the head (last layer + likelihood + ELBO assembly) on bbb_head.cu.
 #include <mutex>
+#include <string>
+#include <vector>
+#include <string.h>
 
 #include "bbb_kernels.h"
 #include "bbb_mlp.h"
@@ -26,6 +29,72 @@ EncodeTiledFn encode_fn() {
 }
 }  // namespace tma
 }  // namespace bbb
+
+// ---- diagnostic: device time of every kernel launched by the network-level calls ------------------------------------
+// (bench.py's roofline: the dominant kernel's duration, measured with CUDA events on the launching stream)
+namespace {
+struct TimedLaunch { char name[48]; cudaEvent_t e0, e1; };
+std::mutex g_tmu;
+bool g_timing = false;
+std::vector<TimedLaunch> g_timed;
+
+struct ScopedTimer {
+  bool on = false;
+  size_t idx = 0;
+  cudaStream_t st;
+  ScopedTimer(const char *fmt, long long a, long long b, cudaStream_t s) : st(s) {
+    std::lock_guard<std::mutex> lk(g_tmu);
+    if (!g_timing) return;
+    TimedLaunch t{};
+    snprintf(t.name, sizeof t.name, fmt, a, b);
+    if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return;
+    cudaEventRecord(t.e0, st);
+    g_timed.push_back(t);
+    idx = g_timed.size() - 1;
+    on = true;
+  }
+  ~ScopedTimer() {
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(g_tmu);
+    if (idx < g_timed.size()) cudaEventRecord(g_timed[idx].e1, st);
+  }
+};
+}  // namespace
+
+extern "C" int bbb_timing_enable(int32_t on) {
+  std::lock_guard<std::mutex> lk(g_tmu);
+  for (auto &t : g_timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  g_timed.clear();
+  g_timing = on != 0;
+  return BBB_OK;
+}
+
+extern "C" int bbb_timing_report(char *buf, int64_t buf_bytes) {
+  BBB_CHECK_ARG(buf && buf_bytes >= 64, "buffer too small");
+  BBB_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_tmu);
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<int> cnt;
+  for (auto &t : g_timed) {
+    float v = 0.0f;
+    if (cudaEventElapsedTime(&v, t.e0, t.e1) != cudaSuccess) continue;
+    size_t k = 0;
+    while (k < names.size() && names[k] != t.name) ++k;
+    if (k == names.size()) { names.push_back(t.name); ms.push_back(0.0); cnt.push_back(0); }
+    ms[k] += v; cnt[k] += 1;
+  }
+  std::string out = "{";
+  for (size_t k = 0; k < names.size(); ++k) {
+    char item[128];
+    snprintf(item, sizeof item, "%s\"%s\": [%.6f, %d]", k ? ", " : "", names[k].c_str(), ms[k], cnt[k]);
+    out += item;
+  }
+  out += "}";
+  if ((int64_t)out.size() + 1 > buf_bytes) return fail(BBB_EINVAL, "bbb_timing_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return BBB_OK;
+}
 
 namespace {
 
@@ -96,14 +165,18 @@ extern "C" int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
     MlpLayerDesc d = make_desc(layers[l], inp, l == 0);
     if (!mlp_fwd_layer_supported(d, S, B))
       return fail(BBB_EUNSUPPORTED, "bbb_mlp_fwd: layer %d needs 16-byte aligned tensors", l);
-    if (int rc = launch_mlp_fwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, flags | BBB_F_RELU_OUT, logp, logq, st))
-      return rc;
+    {
+      ScopedTimer tm("mlp_fwd[%lldx%lld]", (long long)d.in, (long long)d.out, st);
+      if (int rc = launch_mlp_fwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, flags | BBB_F_RELU_OUT, logp, logq, st))
+        return rc;
+    }
     inp = layers[l].act;
   }
   const bbb_mlp_layer &H = layers[n_layers - 1];
   bbb_rng r = rng ? *rng : bbb_rng{};
   r.layer = (uint32_t)(n_layers - 1);
   const int32_t head_flags = flags & (BBB_F_SAMPLE | BBB_F_LOGPROB);      // its input is already the activation
+  ScopedTimer tm("head_fwd[%lldx%lld]", (long long)H.in, (long long)H.out, st);
   return bbb_head_fwd(inp, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b, rng ? &r : nullptr, prior, S, B,
                       H.in, H.out, head_flags, nll_kind, target, sigma, grad_scale, H.act, d_out, logp, logq, nll, beta,
                       beta_dev, out4, done_counter, stream);
@@ -141,6 +214,7 @@ extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
     const bbb_mlp_layer &H = layers[n_layers - 1], &P = layers[n_layers - 2];
     bbb_rng r = rng ? *rng : bbb_rng{};
     r.layer = (uint32_t)(n_layers - 1);
+    ScopedTimer tm("head_bwd[%lldx%lld]", (long long)H.in, (long long)H.out, st);
     if (int rc = bbb_linear_bwd(H.dz, nullptr, P.act, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b,
                                 rng ? &r : nullptr, prior, S, B, H.in, H.out,
                                 keep | BBB_F_RELU_IN | BBB_F_DX_PREACT | BBB_F_OUT_ZEROED, gp, gq, gp_dev, gq_dev,
@@ -154,6 +228,7 @@ extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
     d.dx = l > 0 ? layers[l - 1].dz : nullptr;
     if (!mlp_bwd_layer_supported(d, S, B))
       return fail(BBB_EUNSUPPORTED, "bbb_mlp_bwd: layer %d needs 16-byte aligned tensors", l);
+    ScopedTimer tm("mlp_bwd[%lldx%lld]", (long long)d.in, (long long)d.out, st);
     if (int rc = launch_mlp_bwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, keep, gp, gq, gp_dev, gq_dev,
                                       (int)g_dev_stride, out_scale_dev, st))
       return rc;

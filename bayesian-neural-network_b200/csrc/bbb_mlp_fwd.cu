@@ -180,6 +180,25 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
     const bool row_ok[2] = {r0 < rows, r0 + 64 < rows};
     const uint32_t q_base[2] = {(uint32_t)(o0 + r0) * (uint32_t)a.in4 + (uint32_t)c,
                                 (uint32_t)(o0 + r0 + 64) * (uint32_t)a.in4 + (uint32_t)c};
+    // the tile's bias sample (needed by the finalisation at the very end: computed now, off the tail).  Its log-prob
+    // terms are counted by the pair's first CTA only.
+    if (st < 128 * SG) {
+      const bool sample = MODE != 2;
+      const int s = st >> 7, o_l = st & 127;
+      float bv = 0.0f;
+      if (s < ns && o_l < rows) {
+        const int o = o0 + o_l;
+        const float bmu = __ldg(a.b_mu + o);
+        const float bsg = need_rho ? softplus_f(__ldg(a.b_rho + o)) : 0.0f;
+        float ep = 0.0f;
+        if (sample)
+          ep = MODE == 1 ? __ldg(a.eps_b + (int64_t)(s0 + s) * a.out + o)
+                         : philox_normal1(rng, rng.tensor_b, rng.sample_base + (uint32_t)(s0 + s), (uint64_t)o);
+        bv = sample ? __fadd_rn(bmu, __fmul_rn(bsg, ep)) : bmu;
+        if (kLogProb && part == 0) { lp[s] += logp_elem(a.prior, bv); lq[s] += logq_elem(bsg, ep); }
+      }
+      bias_s[s][o_l] = bv;
+    }
     const uint32_t tiles_u32 = smem_u32(tiles);
     int it = 0;
     for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -255,60 +274,7 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
       }
     }
     tc_fence_before_sync();
-    // ---- completion: the CTA that adds the last partial tile of its pair finalises it -----------------------------------
-    __threadfence();
-    bar_samplers();
-    if (st == 0) {
-      const uint32_t prev = atomicAdd(a.counters + pair, 1u);
-      ctl.is_last = prev + 1u == (uint32_t)cnt;
-    }
-    bar_samplers();
-    if (ctl.is_last) {
-      __threadfence();
-      const bool sample = MODE != 2;
-      if (st < 128 * SG) {
-        const int s = st >> 7, o_l = st & 127;
-        float bv = 0.0f;
-        if (s < ns && o_l < rows) {
-          const int o = o0 + o_l;
-          const float bmu = __ldg(a.b_mu + o);
-          const float bsg = need_rho ? softplus_f(__ldg(a.b_rho + o)) : 0.0f;
-          float ep = 0.0f;
-          if (sample)
-            ep = MODE == 1 ? __ldg(a.eps_b + (int64_t)(s0 + s) * a.out + o)
-                           : philox_normal1(rng, rng.tensor_b, rng.sample_base + (uint32_t)(s0 + s), (uint64_t)o);
-          bv = sample ? __fadd_rn(bmu, __fmul_rn(bsg, ep)) : bmu;
-          if (kLogProb) { lp[s] += logp_elem(a.prior, bv); lq[s] += logq_elem(bsg, ep); }
-        }
-        bias_s[s][o_l] = bv;
-      }
-      bar_samplers();
-      const int nq = rows >> 2, qd = st & 31;
-      const bool relu = a.flags & BBB_F_RELU_OUT;
-      if (qd < nq) {
-        // all loads of a sample first (they are independent), then the stores: one L2 round trip instead of eight
-#pragma unroll
-        for (int s = 0; s < SG; ++s) {
-          if (s >= ns) break;
-          const float4 bq = *reinterpret_cast<const float4 *>(&bias_s[s][qd * 4]);
-          const int64_t off0 = ((int64_t)(s0 + s) * a.B + (st >> 5)) * a.out + o0 + qd * 4;
-          float4 v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if ((st >> 5) + 16 * i < a.B) v[i] = __ldcg(reinterpret_cast<const float4 *>(a.y_pre + off0 + (int64_t)(16 * i) * a.out));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if ((st >> 5) + 16 * i < a.B) {
-              float4 t = v[i];
-              t.x += bq.x; t.y += bq.y; t.z += bq.z; t.w += bq.w;
-              if (relu) t = tcx::relu4(t);
-              *reinterpret_cast<float4 *>(a.act + off0 + (int64_t)(16 * i) * a.out) = t;
-            }
-          }
-        }
-      }
-    }
-    // ---- log-prob sums of this CTA: warp sums -> one fp64 atomic per value ---------------------------------------------
+    // ---- log-prob sums of this CTA: warp sums -> one fp64 atomic per value (before the wait below: off the tail) ------
     if (kLogProb) {
       const int sw = wid - 2;
 #pragma unroll
@@ -316,14 +282,58 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         const float p = warp_sum(lp[s]), q2 = warp_sum(lq[s]);
         if (lane == 0) { red[(2 * s) * kSamplerWarps + sw] = p; red[(2 * s + 1) * kSamplerWarps + sw] = q2; }
       }
-      bar_samplers();
-      if (st < 2 * SG) {
-        const int s = st >> 1, which = st & 1;
-        if (s < ns) {
-          double v = 0.0;
+    }
+    // ---- completion: every CTA of the pair bumps the pair's counter once its partial tile is in memory, waits until all
+    // of them have (the grid is at most one CTA per SM, so all CTAs are co-resident), and finalises ITS slice of the
+    // tile's batch rows: bias + optional ReLU -> the activation.  The finalisation is spread over the pair's CTAs
+    // instead of being the serial tail of the CTA that happens to arrive last.
+    __threadfence();
+    bar_samplers();
+    if (kLogProb && st < 2 * SG) {
+      const int s = st >> 1, which = st & 1;
+      if (s < ns) {
+        double v = 0.0;
 #pragma unroll
-          for (int w8 = 0; w8 < kSamplerWarps; ++w8) v += (double)red[(2 * s + which) * kSamplerWarps + w8];
-          atomicAdd((which ? a.logq : a.logp) + s0 + s, v);
+        for (int w8 = 0; w8 < kSamplerWarps; ++w8) v += (double)red[(2 * s + which) * kSamplerWarps + w8];
+        atomicAdd((which ? a.logq : a.logp) + s0 + s, v);
+      }
+    }
+    if (st == 0) {
+      atomicAdd(a.counters + pair, 1u);
+      uint32_t seen = 0;
+      for (int spin = 0; spin < (1 << 24); ++spin) {     // (bounded: a lost CTA must not hang the GPU)
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counters + pair) : "memory");
+        if (seen >= (uint32_t)cnt) break;
+        __nanosleep(64);
+      }
+    }
+    bar_samplers();
+    {
+      const int b_lo = (int)((int64_t)part * a.B / cnt), b_hi = (int)((int64_t)(part + 1) * a.B / cnt);
+      const int nq = rows >> 2, qd = st & 31;
+      const bool relu = a.flags & BBB_F_RELU_OUT;
+      if (qd < nq) {
+#pragma unroll
+        for (int s = 0; s < SG; ++s) {
+          if (s >= ns) break;
+          const float4 bq = *reinterpret_cast<const float4 *>(&bias_s[s][qd * 4]);
+          for (int bb = b_lo + (st >> 5); bb < b_hi; bb += 16 * 8) {
+            // all loads first (they are independent), then the stores: one L2 round trip
+            const int64_t off0 = ((int64_t)(s0 + s) * a.B + bb) * a.out + o0 + qd * 4;
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (bb + 16 * i < b_hi) v[i] = __ldcg(reinterpret_cast<const float4 *>(a.y_pre + off0 + (int64_t)(16 * i) * a.out));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (bb + 16 * i < b_hi) {
+                float4 t = v[i];
+                t.x += bq.x; t.y += bq.y; t.z += bq.z; t.w += bq.w;
+                if (relu) t = tcx::relu4(t);
+                *reinterpret_cast<float4 *>(a.act + off0 + (int64_t)(16 * i) * a.out) = t;
+              }
+            }
+          }
         }
       }
     }

@@ -490,7 +490,7 @@ class _FusedELBO(torch.autograd.Function):
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
         beta_h, beta_d = _split_beta(beta)
         dims = [params[0][0].shape[1]] + [p[0].shape[0] for p in params]
-        use_mlp = (use_network_level_call and tf32 and mode in ('classification', 'regression') and
+        use_mlp = (use_network_level_call and tf32 and fused_opt is None and mode in ('classification', 'regression') and
                    L.mlp_supported(dims, S, B, L.F_TF32))
         if use_mlp:
             ys, dxs, d_out = _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, beta_h,

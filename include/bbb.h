@@ -290,6 +290,13 @@ int bbb_adam_step_peer(const bbb_peer_comm *comm, float *exp_avg, float *exp_avg
                        double beta1, double beta2, double eps, uint32_t step, const uint32_t *step_dev,
                        const float *lr_scale_dev, void *stream);
 
+/* ---- diagnostic: device time of every kernel the network-level calls launch ------------------------------------------
+ * bbb_timing_enable(1) clears the records and starts bracketing each kernel of bbb_mlp_fwd / bbb_mlp_bwd with CUDA events
+ * on the launching stream (do not enable while a CUDA graph is being captured); bbb_timing_report synchronises the
+ * device and writes a JSON object {"kernel[inxout]": [total ms, launches], ...} into buf (HOST pointer). */
+int bbb_timing_enable(int32_t on);
+int bbb_timing_report(char *buf, int64_t buf_bytes);
+
 /* *counter += inc  (advances a bbb_rng.step_dev between steps; one tiny launch, graph-capturable) */
 int bbb_counter_add(uint32_t *counter, uint32_t inc, void *stream);
 

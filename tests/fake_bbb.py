@@ -382,6 +382,12 @@ class FakeLib:
         p[...] = p - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + eps)
         return 0
 
+    def bbb_timing_enable(self, on):
+        return 0
+
+    def bbb_timing_report(self, buf, n):
+        raise AssertionError('fake lib: no device timing')
+
     def bbb_counter_add(self, counter, inc, st):
         _arr(counter, C.c_uint32, 1)[0] += inc
         return 0
