@@ -81,6 +81,7 @@ struct PriorDev {
   float c1, k1, inv_var1;  // component 1: log(pi) - log(s1) - .5log2pi ; 1/(2 s1^2) ; 1/s1^2
   float c2, k2, inv_var2;  // component 2 (mixture only)
   float c1l, k1l, c2l, k2l;  // c and k times log2(e): the density terms in the base the SFU works in
+  float dkl, dcl;            // k1l - k2l, c2l - c1l: log2 of the component ratio p2/p1 is dkl w^2 + dcl
 };
 
 inline PriorDev make_prior_dev(const bbb_prior *p) {
@@ -103,6 +104,7 @@ inline PriorDev make_prior_dev(const bbb_prior *p) {
   const double l2e = 1.4426950408889634074;
   d.c1l = (float)(d.c1 * l2e); d.k1l = (float)(d.k1 * l2e);
   d.c2l = (float)(d.c2 * l2e); d.k2l = (float)(d.k2 * l2e);
+  d.dkl = (float)(((double)d.k1 - (double)d.k2) * l2e); d.dcl = (float)(((double)d.c2 - (double)d.c1) * l2e);
   return d;
 }
 
@@ -242,14 +244,18 @@ __device__ __forceinline__ float logp_elem_fast(const PriorDev &p, float w) {
   const float m = fmaxf(a, b), d = fminf(a, b) - m;   // exp(max - m) = 1
   return m + __logf(1.0f + __expf(d));
 }
+__device__ __forceinline__ float rcp_approx_f(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// R(w) = (1/s1^2 + t/s2^2) / (1 + t) with t = p2(w)/p1(w) = 2^(dkl w^2 + dcl): one exponential, one reciprocal, no
+// selects.  (t is bounded by its value at w = 0 when s2 < s1; the clamp covers priors given the other way round.)
 __device__ __forceinline__ float prior_R_fast(const PriorDev &p, float w) {
   if (p.kind == BBB_PRIOR_GAUSSIAN) return p.inv_var1;
-  const float w2 = w * w;
-  const float a = fmaf(-p.k1, w2, p.c1), b = fmaf(-p.k2, w2, p.c2);
-  const float t = __expf(-fabsf(a - b));              // smaller responsibility / larger one
-  const float inv = __fdividef(1.0f, 1.0f + t);
-  const float big = a >= b ? p.inv_var1 : p.inv_var2, small = a >= b ? p.inv_var2 : p.inv_var1;
-  return (big + t * small) * inv;
+  float t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fminf(fmaf(p.dkl, w * w, p.dcl), 100.0f)));
+  return fmaf(t, p.inv_var2, p.inv_var1) * rcp_approx_f(1.0f + t);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -279,7 +285,7 @@ __device__ __forceinline__ void softplus_sigmoid_fast(float rho, float &sigma, f
   ser *= t;
   const float lg = 0.6931471805599453f * lg2_approx(u);
   sigma = rho > 15.0f ? rho : (t < 0.125f ? ser : lg);
-  sigmoid = rho > 15.0f ? 1.0f : __fdividef(t, u);
+  sigmoid = rho > 15.0f ? 1.0f : t * rcp_approx_f(u);
 }
 __device__ __forceinline__ float softplus_fast(float rho) {
   float sg, sm;
@@ -290,17 +296,15 @@ __device__ __forceinline__ float softplus_fast(float rho) {
 // weights (the product of two densities cannot underflow for |w| < 9 sigma1); same exp -> mix -> log order as
 // networks.py:24-27.
 __device__ __forceinline__ float logp_quad_fast(const PriorDev &p, const float w[4]) {
-  if (p.kind == BBB_PRIOR_GAUSSIAN) {
-    const float s2 = fmaf(w[0], w[0], fmaf(w[1], w[1], fmaf(w[2], w[2], w[3] * w[3])));
-    return fmaf(-p.k1, s2, 4.0f * p.c1);
-  }
-  float d[4];
+  const float s2 = fmaf(w[0], w[0], fmaf(w[1], w[1], fmaf(w[2], w[2], w[3] * w[3])));
+  if (p.kind == BBB_PRIOR_GAUSSIAN) return fmaf(-p.k1, s2, 4.0f * p.c1);
+  // log2 p(w) = (c1l - k1l w^2) + log2(1 + t),  t = p2/p1 = 2^(dkl w^2 + dcl): ONE exponential per weight and one
+  // logarithm per pair (1 <= 1 + t <= 1 + 2^dcl, so the product of two cannot overflow)
+  float u[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float w2 = w[j] * w[j];
-    d[j] = ex2_approx(fmaf(-p.k1l, w2, p.c1l)) + ex2_approx(fmaf(-p.k2l, w2, p.c2l));
-  }
-  return 0.6931471805599453f * (lg2_approx(d[0] * d[1]) + lg2_approx(d[2] * d[3]));
+  for (int j = 0; j < 4; ++j) u[j] = 1.0f + ex2_approx(fminf(fmaf(p.dkl, w[j] * w[j], p.dcl), 60.0f));
+  const float lg = lg2_approx(u[0] * u[1]) + lg2_approx(u[2] * u[3]);
+  return 0.6931471805599453f * (fmaf(-p.k1l, s2, 4.0f * p.c1l) + lg);
 }
 // sum of log sigma_j over a quad: one lg2 per pair (sigma > 1e-19 keeps the product normal)
 __device__ __forceinline__ float logsigma_quad_fast(const float sg[4]) {

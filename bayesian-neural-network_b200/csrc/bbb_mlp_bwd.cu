@@ -228,8 +228,8 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         }
         csum[s][o_l] = acc;
       }
-      mbar_wait(smem_u32(&ctl.murho_full), gph);
-      mbar_wait(smem_u32(&ctl.g_full), gph);
+      mbar_wait_parked(smem_u32(&ctl.murho_full), gph);     // (parked: a spinning warp would take issue slots from the
+      mbar_wait_parked(smem_u32(&ctl.g_full), gph);         //  TMA and MMA warps, which have the lowest priority)
       tc_fence_after_sync();
       if (bias_cta) {
         bar_epi();
@@ -272,7 +272,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               softplus_sigmoid_fast(rho[e], sg[e], sgm[e]);
-              isg[e] = __fdividef(1.0f, sg[e]);
+              isg[e] = rcp_approx_f(sg[e]);
             }
             const uint32_t quad = (uint32_t)(o_t0 + row) * (uint32_t)nq_i + (uint32_t)(q_lo + qd);
 #pragma unroll
@@ -335,14 +335,27 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive_l(smem_u32(&ctl.w_full));
         for (int s = 0; s < ns; ++s) {
-          mbar_wait(smem_u32(&ctl.dx_full[s]), gph);
+          // the activations this layer consumed (the (x > 0) mask), in the coalesced mapping: requested before the wait
+          float4 xm[XWR][2];
+#pragma unroll
+          for (int r = 0; r < XWR; ++r)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int b = c_row + 64 * hh, qd = 8 * r + c_chk;
+              xm[r][hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (qd < tq && b < a.B)
+                xm[r][hh] = __ldg(reinterpret_cast<const float4 *>(a.x + ((int64_t)(s0 + s) * a.B + b) * a.in + i_lo + 4 * qd));
+            }
+          mbar_wait_parked(smem_u32(&ctl.dx_full[s]), gph);
           tc_fence_after_sync();
-#pragma unroll 1
+#pragma unroll
           for (int r = 0; r < XWR; ++r) {
             float v[8];
             tmem_ld8(tm_dx[s] + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * r + 8 * cgp), v);
-            sts128(stg + stg_off(row, 2 * cgp), v[0], v[1], v[2], v[3]);
-            sts128(stg + stg_off(row, 2 * cgp + 1), v[4], v[5], v[6], v[7]);
+            // two staging tiles, used alternately: one barrier per region instead of two
+            const uint32_t sg_t = stg + (uint32_t)((r & 1) * REG);
+            sts128(sg_t + stg_off(row, 2 * cgp), v[0], v[1], v[2], v[3]);
+            sts128(sg_t + stg_off(row, 2 * cgp + 1), v[4], v[5], v[6], v[7]);
             bar_epi();
             const int qd = 8 * r + c_chk;
             if (qd < tq) {
@@ -351,15 +364,13 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
                 const int b = c_row + 64 * hh;
                 if (b < a.B) {
                   const int64_t e = ((int64_t)(s0 + s) * a.B + b) * a.in + i_lo + 4 * qd;
-                  float4 d = lds128(stg + stg_off(b, c_chk));
-                  const float4 xm = __ldg(reinterpret_cast<const float4 *>(a.x + e));   // the activation this layer consumed
-                  d = tcx::mask4(d, xm);
+                  const float4 d = tcx::mask4(lds128(sg_t + stg_off(b, c_chk)), xm[r][hh]);
                   tcx::red_add_v4(a.dx + e, d);
                 }
               }
             }
-            bar_epi();
           }
+          bar_epi();      // (the staging tiles are rewritten by the next sample)
         }
       }
       tc_fence_before_sync();

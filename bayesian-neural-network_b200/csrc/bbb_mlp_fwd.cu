@@ -82,7 +82,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 template <int SG, int MODE, bool kLogProb>
 __global__ void __launch_bounds__(kThreads, 1)
 ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__ CUtensorMap tm_rho,
-              const __grid_constant__ CUtensorMap tm_x, const MlpFwdArgs a) {
+              const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const MlpFwdArgs a) {
   using Cfg = FwdCfg<SG>;
   constexpr int NS = Cfg::kStages;
   extern __shared__ uint8_t dsm[];
@@ -119,6 +119,7 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
     tma::prefetch_map(&tm_mu);
     if (need_rho) tma::prefetch_map(&tm_rho);
     tma::prefetch_map(&tm_x);
+    tma::prefetch_map(&tm_y);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -250,28 +251,39 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
     }
     pdl_launch_dependents();
 
-    // ---- drain: TMEM [lane = o][column = b] -> coalesced red.add into the pre-activation scratch --------------------
-    // Accumulator lanes beyond the tile's rows and columns beyond the batch hold exact zeros (zero weight rows above,
-    // zero-filled activation rows from the TMA), so every lane adds unconditionally -- to a clamped address where its own
-    // does not exist -- and the loop carries neither predicates nor branches.
+    // ---- drain: TMEM [lane = o][column = b] -> shared staging [b][o] -> ONE bulk reduce-add per sample ----------------
+    // The operand ring is idle now: stage s holds sample s's partial tile as a plain [128 b][128 o] fp32 matrix (a warp
+    // writes 32 consecutive o of one batch row: conflict-free, immediate offsets), and the TMA engine adds it to the
+    // zero-filled pre-activation scratch in L2 (cp.reduce.async.bulk.tensor .add): no per-thread atomics, no address
+    // arithmetic; rows beyond the batch and columns beyond `out` are dropped by the TMA, accumulator lanes beyond the
+    // tile's rows hold exact zeros (zero weight rows above).
     mbar_wait(smem_u32(&ctl.acc_full), 0u);
     tc_fence_after_sync();
     {
       const int q = wid & 3, cg = (wid - 2) >> 2;          // TMEM lane quarter of this warp, 32-column group
-      const int o_l = min(q * 32 + lane, rows - 1);
+      const uint32_t srow = tiles_u32 + (uint32_t)((q * 32 + lane) * 4 + cg * 32 * 512);
 #pragma unroll
       for (int s = 0; s < SG; ++s) {
         if (s >= ns) break;
-        const float *yp = a.y_pre + ((int64_t)(s0 + s) * a.B) * a.out + o0 + o_l;
 #pragma unroll
         for (int cb = 0; cb < 32; cb += 16) {
           float v[16];
           tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128 + cg * 32 + cb), v);
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj)
-            red_add_f32(yp + (uint32_t)min(cg * 32 + cb + jj, a.B - 1) * (uint32_t)a.out, v[jj]);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(srow + (uint32_t)(s * Cfg::kStage + (cb + jj) * 512)), "f"(v[jj]) : "memory");
         }
       }
+    }
+    tc_fence_before_sync();
+    fence_proxy_async_smem();
+    bar_samplers();
+    if (st == 0) {
+#pragma unroll
+      for (int s = 0; s < SG; ++s)
+        if (s < ns) tma::reduce_add_3d(&tm_y, tiles_u32 + (uint32_t)(s * Cfg::kStage), o0, 0, s0 + s);
+      tma::bulk_commit();
+      tma::bulk_wait_all();         // the adds are performed: the counter below may announce them
     }
     tc_fence_before_sync();
     // ---- log-prob sums of this CTA: warp sums -> one fp64 atomic per value (before the wait below: off the tail) ------
@@ -344,21 +356,19 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
 }
 
 template <int SG, int MODE, bool kLogProb>
-int launch_one(const CUtensorMap &tm_mu, const CUtensorMap &tm_rho, const CUtensorMap &tm_x, const MlpFwdArgs &a, int grid,
-               cudaStream_t st) {
+int launch_one(const CUtensorMap *tm, const MlpFwdArgs &a, int grid, cudaStream_t st) {
   auto kernel = ws_fwd_kernel<SG, MODE, kLogProb>;
   BBB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<SG>::kDyn));
-  BBB_CHECK_CUDA(launch_pdl(kernel, dim3(grid), dim3(kThreads), (size_t)FwdCfg<SG>::kDyn, st, tm_mu, tm_rho, tm_x, a));
+  BBB_CHECK_CUDA(launch_pdl(kernel, dim3(grid), dim3(kThreads), (size_t)FwdCfg<SG>::kDyn, st, tm[0], tm[1], tm[2], tm[3], a));
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }
 
 template <int SG>
-int launch_sg(const CUtensorMap &tm_mu, const CUtensorMap &tm_rho, const CUtensorMap &tm_x, const MlpFwdArgs &a, int grid,
-              int mode, bool lpq, cudaStream_t st) {
-  if (mode == 0) return lpq ? launch_one<SG, 0, true>(tm_mu, tm_rho, tm_x, a, grid, st) : launch_one<SG, 0, false>(tm_mu, tm_rho, tm_x, a, grid, st);
-  if (mode == 1) return lpq ? launch_one<SG, 1, true>(tm_mu, tm_rho, tm_x, a, grid, st) : launch_one<SG, 1, false>(tm_mu, tm_rho, tm_x, a, grid, st);
-  return lpq ? launch_one<SG, 2, true>(tm_mu, tm_rho, tm_x, a, grid, st) : launch_one<SG, 2, false>(tm_mu, tm_rho, tm_x, a, grid, st);
+int launch_sg(const CUtensorMap *tm, const MlpFwdArgs &a, int grid, int mode, bool lpq, cudaStream_t st) {
+  if (mode == 0) return lpq ? launch_one<SG, 0, true>(tm, a, grid, st) : launch_one<SG, 0, false>(tm, a, grid, st);
+  if (mode == 1) return lpq ? launch_one<SG, 1, true>(tm, a, grid, st) : launch_one<SG, 1, false>(tm, a, grid, st);
+  return lpq ? launch_one<SG, 2, true>(tm, a, grid, st) : launch_one<SG, 2, false>(tm, a, grid, st);
 }
 
 inline int cdiv_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -393,13 +403,14 @@ int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngD
   int grid = sm_count();
   if ((int64_t)pairs * a.nkb < grid) grid = pairs * a.nkb;
   a.base = grid / pairs; a.rem = grid % pairs;
-  CUtensorMap tm_mu, tm_rho, tm_x;
-  if (int r = tma::make_map(&tm_mu, l.w_mu, l.in, l.out, 0, 32, 128, tma::kNone)) return r;
-  tm_rho = tm_mu;
+  CUtensorMap tm[4];
+  if (int r = tma::make_map(&tm[0], l.w_mu, l.in, l.out, 0, 32, 128, tma::kNone)) return r;
+  tm[1] = tm[0];
   if (l.w_rho)
-    if (int r = tma::make_map(&tm_rho, l.w_rho, l.in, l.out, 0, 32, 128, tma::kNone)) return r;
-  if (int r = tma::make_map(&tm_x, l.x, l.in, B, l.x_shared ? 1 : S, 32, 128, tma::kSw128)) return r;
-  return sg == 2 ? launch_sg<2>(tm_mu, tm_rho, tm_x, a, grid, mode, lpq, st) : launch_sg<1>(tm_mu, tm_rho, tm_x, a, grid, mode, lpq, st);
+    if (int r = tma::make_map(&tm[1], l.w_rho, l.in, l.out, 0, 32, 128, tma::kNone)) return r;
+  if (int r = tma::make_map(&tm[2], l.x, l.in, B, l.x_shared ? 1 : S, 32, 128, tma::kSw128)) return r;
+  if (int r = tma::make_map(&tm[3], l.y_pre, l.out, B, S, 128, 128, tma::kNone)) return r;   // split-K reduce-add target
+  return sg == 2 ? launch_sg<2>(tm, a, grid, mode, lpq, st) : launch_sg<1>(tm, a, grid, mode, lpq, st);
 }
 
 }  // namespace bbb

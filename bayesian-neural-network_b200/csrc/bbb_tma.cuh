@@ -62,5 +62,14 @@ __device__ __forceinline__ void load_3d(uint32_t smem_dst, const CUtensorMap *m,
                ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// shared -> global reduction: every element of the [1][box1][box0] tile at `smem_src` is ADDED to the tensor (fp32 add
+// performed in L2; elements outside the tensor are dropped).  Bulk-group completion: commit, then wait.
+__device__ __forceinline__ void reduce_add_3d(const CUtensorMap *m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(m), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 }  // namespace tma
 }  // namespace bbb
