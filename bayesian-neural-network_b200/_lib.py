@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get('BBB_LIB') or os.path.join(_HERE, 'libbbb.so')   # BBB
 
 # flags (include/bbb.h)
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
-F_OUT_ZEROED, F_DX_PREACT, F_RELU_OUT = 256, 512, 1024
+F_OUT_ZEROED, F_DX_PREACT = 256, 512
 PRIOR_GAUSSIAN, PRIOR_MIXTURE = 0, 1
 NLL_NONE, NLL_CE, NLL_GAUSS = 0, 1, 2
 
@@ -41,7 +41,7 @@ class MlpLayer(C.Structure):
     """struct bbb_mlp_layer: one layer of a network-level call (bbb_mlp_fwd / bbb_mlp_bwd)"""
     _fields_ = [('w_mu', C.c_void_p), ('w_rho', C.c_void_p), ('b_mu', C.c_void_p), ('b_rho', C.c_void_p),
                 ('eps_w', C.c_void_p), ('eps_b', C.c_void_p), ('inn', C.c_int64), ('out', C.c_int64),
-                ('y_pre', C.c_void_p), ('act', C.c_void_p), ('counters', C.c_void_p), ('dz', C.c_void_p),
+                ('y', C.c_void_p), ('dz', C.c_void_p),
                 ('g_w_mu', C.c_void_p), ('g_w_rho', C.c_void_p), ('g_b_mu', C.c_void_p), ('g_b_rho', C.c_void_p)]
 
 
@@ -75,6 +75,7 @@ _SIGS = {
     'bbb_adam_step_peer': ([P, P, P, I64, F64, F64, F64, F64, U32, P, P, P], C.c_int),
     'bbb_counter_add': ([P, U32, P], C.c_int),
     'bbb_timing_enable': ([I32], C.c_int),
+    'bbb_debug_set_timeline': ([P], C.c_int),
     'bbb_timing_report': ([C.c_char_p, I64], C.c_int),
 }
 EXPORTS = tuple(_SIGS)

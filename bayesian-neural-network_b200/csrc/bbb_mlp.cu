@@ -14,6 +14,22 @@
 using namespace bbb;
 
 namespace bbb {
+namespace {
+unsigned long long *g_timeline = nullptr;
+int g_timeline_launch = 0;
+}
+// (every launch gets its own 160 x 16 slice of the buffer, 8 slices, in launch order)
+unsigned long long *debug_timeline() { return g_timeline ? g_timeline + (size_t)(g_timeline_launch++ % 8) * 2560 : nullptr; }
+}  // namespace bbb
+
+// debug aid (tools/kernel_timeline.py): every CTA of the NEXT network-level kernels writes 16 globaltimer stamps into buf
+extern "C" int bbb_debug_set_timeline(unsigned long long *buf) {
+  bbb::g_timeline = buf;
+  bbb::g_timeline_launch = 0;
+  return BBB_OK;
+}
+
+namespace bbb {
 namespace tma {
 EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -119,7 +135,7 @@ MlpLayerDesc make_desc(const bbb_mlp_layer &L, const float *x, bool x_shared) {
   d.x = x; d.x_shared = x_shared;
   d.w_mu = L.w_mu; d.w_rho = L.w_rho; d.b_mu = L.b_mu; d.b_rho = L.b_rho; d.eps_w = L.eps_w; d.eps_b = L.eps_b;
   d.in = L.in; d.out = L.out;
-  d.y_pre = L.y_pre; d.act = L.act; d.counters = L.counters;
+  d.y = L.y;
   d.dz = L.dz; d.g_w_mu = L.g_w_mu; d.g_w_rho = L.g_w_rho; d.g_b_mu = L.g_b_mu; d.g_b_rho = L.g_b_rho;
   return d;
 }
@@ -145,11 +161,10 @@ extern "C" int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
   dims[0] = layers[0].in;
   for (int l = 0; l < n_layers; ++l) {
     const bbb_mlp_layer &L = layers[l];
-    BBB_CHECK_ARG(L.w_mu && L.b_mu && L.act, "null layer pointer");
+    BBB_CHECK_ARG(L.w_mu && L.b_mu && L.y, "null layer pointer");
     BBB_CHECK_ARG(!(sample || lpq) || (L.w_rho && L.b_rho), "rho pointers required");
     BBB_CHECK_ARG(!sample || (L.eps_w && L.eps_b) || (!L.eps_w && !L.eps_b && rng), "give both eps pointers or an rng");
     BBB_CHECK_ARG(L.in == dims[l], "layer widths do not chain");
-    BBB_CHECK_ARG(l + 1 == n_layers || (L.y_pre && L.counters), "hidden layers need y_pre and counters");
     dims[l + 1] = L.out;
   }
   if (!dims_supported(dims, n_layers, S, B) || !tma::encode_fn())
@@ -167,18 +182,18 @@ extern "C" int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
       return fail(BBB_EUNSUPPORTED, "bbb_mlp_fwd: layer %d needs 16-byte aligned tensors", l);
     {
       ScopedTimer tm("mlp_fwd[%lldx%lld]", (long long)d.in, (long long)d.out, st);
-      if (int rc = launch_mlp_fwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, flags | BBB_F_RELU_OUT, logp, logq, st))
-        return rc;
+      const int32_t lf = (flags & (BBB_F_SAMPLE | BBB_F_LOGPROB | BBB_F_TF32)) | (l > 0 ? BBB_F_RELU_IN : 0);
+      if (int rc = launch_mlp_fwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, lf, logp, logq, st)) return rc;
     }
-    inp = layers[l].act;
+    inp = layers[l].y;
   }
   const bbb_mlp_layer &H = layers[n_layers - 1];
   bbb_rng r = rng ? *rng : bbb_rng{};
   r.layer = (uint32_t)(n_layers - 1);
-  const int32_t head_flags = flags & (BBB_F_SAMPLE | BBB_F_LOGPROB);      // its input is already the activation
+  const int32_t head_flags = (flags & (BBB_F_SAMPLE | BBB_F_LOGPROB)) | BBB_F_RELU_IN;    // its input is a pre-activation
   ScopedTimer tm("head_fwd[%lldx%lld]", (long long)H.in, (long long)H.out, st);
   return bbb_head_fwd(inp, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b, rng ? &r : nullptr, prior, S, B,
-                      H.in, H.out, head_flags, nll_kind, target, sigma, grad_scale, H.act, d_out, logp, logq, nll, beta,
+                      H.in, H.out, head_flags, nll_kind, target, sigma, grad_scale, H.y, d_out, logp, logq, nll, beta,
                       beta_dev, out4, done_counter, stream);
 }
 
@@ -199,7 +214,7 @@ extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
                   "null layer pointer");
     BBB_CHECK_ARG(!sample || (L.eps_w && L.eps_b) || (!L.eps_w && !L.eps_b && rng), "give both eps pointers or an rng");
     BBB_CHECK_ARG(L.in == dims[l], "layer widths do not chain");
-    BBB_CHECK_ARG(l + 1 == n_layers || L.act, "hidden layers need their stored activation");
+    BBB_CHECK_ARG(l + 1 == n_layers || L.y, "hidden layers need their stored pre-activation");
     dims[l + 1] = L.out;
   }
   if (!dims_supported(dims, n_layers, S, B) || !tma::encode_fn())
@@ -209,13 +224,13 @@ extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
   PriorDev pd{};
   if (prior) pd = make_prior_dev(prior);
   const int32_t keep = flags & (BBB_F_SAMPLE | BBB_F_TF32 | BBB_F_ACCUM);
-  // the head: dz of the last hidden layer = (d_out W_s) (act > 0), added into its zero-filled buffer
+  // the head: dz of the last hidden layer = (d_out W_s) (y > 0), added into its zero-filled buffer
   {
     const bbb_mlp_layer &H = layers[n_layers - 1], &P = layers[n_layers - 2];
     bbb_rng r = rng ? *rng : bbb_rng{};
     r.layer = (uint32_t)(n_layers - 1);
     ScopedTimer tm("head_bwd[%lldx%lld]", (long long)H.in, (long long)H.out, st);
-    if (int rc = bbb_linear_bwd(H.dz, nullptr, P.act, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b,
+    if (int rc = bbb_linear_bwd(H.dz, nullptr, P.y, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b,
                                 rng ? &r : nullptr, prior, S, B, H.in, H.out,
                                 keep | BBB_F_RELU_IN | BBB_F_DX_PREACT | BBB_F_OUT_ZEROED, gp, gq, gp_dev, gq_dev,
                                 g_dev_stride, out_scale_dev, P.dz, H.g_w_mu, H.g_w_rho, H.g_b_mu, H.g_b_rho, stream))
@@ -224,12 +239,12 @@ extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
   for (int l = n_layers - 2; l >= 0; --l) {
     bbb_rng r = rng ? *rng : bbb_rng{};
     r.layer = (uint32_t)l;
-    MlpLayerDesc d = make_desc(layers[l], l > 0 ? layers[l - 1].act : x, l == 0);
+    MlpLayerDesc d = make_desc(layers[l], l > 0 ? layers[l - 1].y : x, l == 0);
     d.dx = l > 0 ? layers[l - 1].dz : nullptr;
     if (!mlp_bwd_layer_supported(d, S, B))
       return fail(BBB_EUNSUPPORTED, "bbb_mlp_bwd: layer %d needs 16-byte aligned tensors", l);
     ScopedTimer tm("mlp_bwd[%lldx%lld]", (long long)d.in, (long long)d.out, st);
-    if (int rc = launch_mlp_bwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, keep, gp, gq, gp_dev, gq_dev,
+    if (int rc = launch_mlp_bwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, keep | (l > 0 ? BBB_F_RELU_IN : 0), gp, gq, gp_dev, gq_dev,
                                       (int)g_dev_stride, out_scale_dev, st))
       return rc;
   }

@@ -7,23 +7,19 @@ namespace bbb {
 
 // one weight-sampling layer inside a network-level call
 struct MlpLayerDesc {
-  const float *x;            // forward input  [S,B,in], or [B,in] when x_shared (the network's input)
-  bool x_shared;
+  const float *x;            // forward input [S,B,in]: the PRE-activation output of the layer below (ReLU is applied to the
+  bool x_shared;             // loaded tiles in shared memory), or [B,in] when x_shared (the network's input, no ReLU)
   const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_w, *eps_b;
   int64_t in, out;
-  float *y_pre;              // [S,B,out] zero-filled scratch: split-K partial sums of the pre-activation
-  float *act;                // [S,B,out] the layer's output (bias added, ReLU applied when BBB_F_RELU_OUT)
-  uint32_t *counters;        // zero-filled completion counters, one per (sample group, output-row tile)
+  float *y;                  // [S,B,out] zero-filled: the pre-activation output, split-K partial tiles are reduce-added into it
   // backward
   const float *dz;           // [S,B,out] gradient w.r.t. the layer's pre-activation output
-  float *dx;                 // [S,B,in] zero-filled: gradient w.r.t. the PRE-activation input (masked by x > 0), or NULL
+  float *dx;                 // [S,B,in] zero-filled: gradient w.r.t. the pre-activation input (masked by x > 0), or NULL
   float *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;
 };
 
 struct MlpFwdArgs {
   const float *b_mu, *b_rho, *eps_w, *eps_b;
-  float *y_pre, *act;
-  uint32_t *counters;
   double *logp, *logq;
   RngDev rng;
   PriorDev prior;
@@ -31,6 +27,7 @@ struct MlpFwdArgs {
   int n_ot, T_o, nkb;        // output-row tiles of T_o rows; 32-wide k blocks
   int base, rem;             // CTA -> (pair, part): the first `rem` pairs get base + 1 CTAs, the others base
   int flags, x_shared;
+  unsigned long long *timeline;   // debug (bbb_debug_set_timeline): 16 globaltimer stamps per CTA, or NULL
 };
 
 struct MlpBwdArgs {
@@ -47,7 +44,18 @@ struct MlpBwdArgs {
   float gp, gq;              // d loss / d logp_s, d loss / d logq_s (host factors) ...
   const float *gp_dev, *gq_dev, *out_scale_dev;   // ... times optional device scalars (bbb_linear_bwd semantics)
   int g_dev_stride;
+  unsigned long long *timeline;   // debug: 16 globaltimer stamps per CTA, or NULL
 };
+
+// debug: phase time stamps of the network-level kernels (tools/kernel_timeline.py)
+unsigned long long *debug_timeline();
+__device__ __forceinline__ void stamp(unsigned long long *tl, int slot) {
+  if (tl) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
+  }
+}
 
 bool mlp_fwd_layer_supported(const MlpLayerDesc &l, int64_t S, int64_t B);
 int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngDev &rng, const PriorDev &prior, int flags,

@@ -47,7 +47,7 @@ struct BwdCfg {
 };
 
 struct BwdCtl {
-  uint64_t murho_full, ring_full[NRING], ring_empty[NRING], g_full, dzk_full, w_full, dx_full[2], tail_done;
+  uint64_t murho_full, ring_full[NRING], ring_fixed[NRING], ring_empty[NRING], g_full, dzk_full, w_full, dx_full[2], tail_done;
   uint32_t tmem_base;
 };
 
@@ -83,6 +83,8 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
   const uint32_t area = base + 2 * Cfg::kW;              // MMA1 ring, later dz K-major (4 REG) + staging (2 REG)
   const uint32_t dzk = area, stg = area + 4 * REG;
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  unsigned long long *tl = tid == 64 ? a.timeline : nullptr;     // the first epilogue thread stamps the phases (group 0)
+  stamp(tl, 0);
 
   // ---- this CTA's block ----------------------------------------------------------------------------------------------
   const int ot = blockIdx.y;
@@ -96,7 +98,10 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
   if (wid == 1) tmem_alloc(smem_u32(&ctl.tmem_base), 512);
   if (tid == 0) {
     mbar_init(smem_u32(&ctl.murho_full), 1);
-    for (int i = 0; i < NRING; ++i) { mbar_init(smem_u32(&ctl.ring_full[i]), 1); mbar_init(smem_u32(&ctl.ring_empty[i]), 1); }
+    for (int i = 0; i < NRING; ++i) {
+      mbar_init(smem_u32(&ctl.ring_full[i]), 1); mbar_init(smem_u32(&ctl.ring_empty[i]), 1);
+      mbar_init(smem_u32(&ctl.ring_fixed[i]), kEpiWarps);
+    }
     mbar_init(smem_u32(&ctl.g_full), 1);
     mbar_init(smem_u32(&ctl.dzk_full), 1);
     mbar_init(smem_u32(&ctl.w_full), kEpiWarps);
@@ -112,7 +117,11 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem = ctl.tmem_base;
   const uint32_t tm_g[2] = {tmem, tmem + 96}, tm_dx[2] = {tmem + 192, tmem + 288};
-  pdl_wait();
+  stamp(tl, 1);
+  const bool relu_in = a.flags & BBB_F_RELU_IN;      // x is the pre-activation of the layer below: max(., 0) in shared memory
+  // (mu / rho are written by the optimiser only: the producer requests the block's tiles before the dependency wait)
+  if (wid != 0) pdl_wait();
+  stamp(tl, 2);
 
   if (wid == 0) {
     // ================================ TMA producer ====================================================================
@@ -129,6 +138,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
           tma::load_2d(w_s[0] + r * REG, &tm_mu, smem_u32(&ctl.murho_full), i_lo + 32 * r, o_t0);
           tma::load_2d(w_s[1] + r * REG, &tm_rho, smem_u32(&ctl.murho_full), i_lo + 32 * r, o_t0);
         }
+        if (g == 0) pdl_wait();
         // MMA1 operands: per sample 4 chunks of 32 batch rows, dz [4 o groups] + x [XWR i groups]
         for (int s = 0; s < ns; ++s) {
           for (int ch = 0; ch < 4; ++ch, ++rit) {
@@ -155,6 +165,8 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
           }
         }
       }
+    } else {
+      pdl_wait();
     }
     __syncwarp();
     pdl_launch_dependents();
@@ -171,6 +183,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
           for (int ch = 0; ch < 4; ++ch, ++rit) {
             const int slot = rit % NRING;
             mbar_wait_parked(smem_u32(&ctl.ring_full[slot]), (uint32_t)((rit / NRING) & 1));
+            if (relu_in) mbar_wait_parked(smem_u32(&ctl.ring_fixed[slot]), (uint32_t)((rit / NRING) & 1));
             tc_fence_after_sync();
             const uint32_t cb = area + slot * Cfg::kChunk;
 #pragma unroll
@@ -208,6 +221,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
     const float osc = a.out_scale_dev ? __ldg(a.out_scale_dev) : 1.0f;
     const bool accum_flag = a.flags & BBB_F_ACCUM;
     const int c_row = et >> 3, c_chk = et & 7;            // coalesced mapping: rows c_row + 64 h, 16-byte chunk c_chk
+    int erit = 0;                                          // MMA1 chunk counter (the ring's iteration index)
     for (int g = 0; g < groups; ++g) {
       const int s0 = 2 * g, ns = min(2, a.S - s0);
       const uint32_t gph = (uint32_t)(g & 1);
@@ -217,6 +231,22 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         const int si = min(s0 + s, a.S - 1);
         gps[s] = a.gp * (a.gp_dev ? __ldg(a.gp_dev + si * a.g_dev_stride) : 1.0f);
         gqs[s] = a.gq * (a.gq_dev ? __ldg(a.gq_dev + si * a.g_dev_stride) : 1.0f);
+      }
+      if (relu_in) {
+        // the x part of every MMA1 chunk holds PRE-activations: max(., 0) in place, chunk by chunk as they land
+        // (XWR regions of [32 rows][128 B]: 256 16-byte quads each; elementwise, so the swizzle does not matter)
+        for (int c8 = 0; c8 < 4 * ns; ++c8, ++erit) {
+          const int slot = erit % NRING;
+          mbar_wait_parked(smem_u32(&ctl.ring_full[slot]), (uint32_t)((erit / NRING) & 1));
+          const uint32_t xb = area + slot * Cfg::kChunk + 4 * CH_REG;
+          for (int i = et; i < XWR * 256; i += kEpi) {
+            const float4 v = lds128(xb + i * 16);
+            sts128(xb + i * 16, fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_l(smem_u32(&ctl.ring_fixed[slot]));
+        }
       }
       // ---- bias gradients (the CTAs of column range 0): column sums of dz over the batch, then the analytic terms ----
       if (bias_cta && et < 256) {
@@ -229,8 +259,10 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         csum[s][o_l] = acc;
       }
       mbar_wait_parked(smem_u32(&ctl.murho_full), gph);     // (parked: a spinning warp would take issue slots from the
+      if (g == 0) stamp(tl, 3);
       mbar_wait_parked(smem_u32(&ctl.g_full), gph);         //  TMA and MMA warps, which have the lowest priority)
       tc_fence_after_sync();
+      if (g == 0) stamp(tl, 4);
       if (bias_cta) {
         bar_epi();
         if (et < rows) {
@@ -327,6 +359,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
           }
         }
         bar_epi();      // the staging tiles are rewritten by the next region
+        if (g == 0 && r < 3) stamp(tl, 5 + r);
       }
       if (kDx) {
         // ---- dgrad: the weight tiles are complete -> MMA2; then dX_s [lane = b][column = i] -> mask -> red.add ------------
@@ -334,6 +367,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_l(smem_u32(&ctl.w_full));
+        if (g == 0) stamp(tl, 8);
         for (int s = 0; s < ns; ++s) {
           // the activations this layer consumed (the (x > 0) mask), in the coalesced mapping: requested before the wait
           float4 xm[XWR][2];
@@ -348,6 +382,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
             }
           mbar_wait_parked(smem_u32(&ctl.dx_full[s]), gph);
           tc_fence_after_sync();
+          if (g == 0) stamp(tl, 9 + 2 * s);
 #pragma unroll
           for (int r = 0; r < XWR; ++r) {
             float v[8];
@@ -371,6 +406,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
             }
           }
           bar_epi();      // (the staging tiles are rewritten by the next sample)
+          if (g == 0) stamp(tl, 10 + 2 * s);
         }
       }
       tc_fence_before_sync();
@@ -379,6 +415,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
     }
     pdl_launch_dependents();
   }
+  stamp(tl, 15);
   tc_fence_before_sync();
   __syncthreads();
   if (wid == 1) tmem_dealloc(tmem, 512);
@@ -428,6 +465,7 @@ int launch_mlp_bwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngD
   a.T_o = ((cdiv_i(l.out, a.n_ot) + 3) / 4) * 4;
   a.n_ot = cdiv_i(l.out, a.T_o);
   a.flags = flags; a.x_shared = l.x_shared ? 1 : 0;
+  a.timeline = debug_timeline();
   a.gp = gp; a.gq = gq; a.gp_dev = gp_dev; a.gq_dev = gq_dev; a.g_dev_stride = g_dev_stride; a.out_scale_dev = out_scale_dev;
   const int nq_i = (int)(l.in / 4);
   int n_c = sm_count() / a.n_ot;                                   // about one CTA per SM

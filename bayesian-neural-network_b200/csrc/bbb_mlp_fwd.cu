@@ -13,12 +13,14 @@
 //     quad into the SWIZZLE_128B weight tile.  Two quads x SG samples per thread and stage: straight-line code;
 //   * warp 1 (one lane) issues the MMAs and releases stages with tcgen05.commit.
 // Work split: the weight matrix is cut into (sample group, tile of T_o <= 128 output rows) pairs and every pair's k blocks
-// are divided over its share of the one-CTA-per-SM grid, so a CTA owns ONE accumulator segment.  It adds its partial
-// tile to the zero-filled pre-activation scratch with coalesced red.global.add.f32 (measured on B200: as fast as plain
-// stores, tools/b200_probe.cu) and bumps the pair's completion counter; the CTA that arrives last finalises the tile:
-// bias sample (+ its log-prob terms), optional ReLU, and a plain store of the ACTIVATION the next layer's TMA loads.
-// Hence the layer's consumers never apply ReLU or TF32 conversion while staging, which is what made the round-1 kernels
-// instruction-bound.
+// are divided over its share of the one-CTA-per-SM grid, so a CTA owns ONE accumulator segment.  It drains the segment
+// TMEM -> registers -> a plain [128 b][128 o] shared-memory tile (the operand ring is idle by then) and hands it to the
+// TMA engine, which ADDS it to the zero-filled pre-activation output in L2 (cp.reduce.async.bulk.tensor): the split-K
+// combine costs no per-thread atomics and no address arithmetic.  The pair's first CTA adds the sampled bias to its
+// partial tile, so the output is the complete pre-activation once every CTA has finished -- no completion protocol.
+// ReLU belongs to the consumer: when the input is a hidden layer's pre-activation (BBB_F_RELU_IN) the samplers apply
+// max(x, 0) IN PLACE to the activation tiles the TMA has just loaded (two 16-byte chunks per thread and tile, ~1 % of the
+// sampling work); the tensor core reads them as TF32 by truncation.
 #include "bbb_tc_tiles.cuh"
 #include "bbb_tma.cuh"
 #include "bbb_mlp.h"
@@ -44,7 +46,6 @@ struct FwdCfg {
 struct FwdCtl {
   uint64_t full_in[3], full_w[3], empty[3], acc_full;
   uint32_t tmem_base;
-  int is_last;
 };
 
 __device__ __forceinline__ void bar_samplers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -91,6 +92,8 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
   __shared__ float red[2 * SG * kSamplerWarps];
   uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(dsm) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  unsigned long long *tl = tid == 64 ? a.timeline : nullptr;     // the first sampler thread stamps the phases
+  stamp(tl, 0);
 
   // ---- this CTA's segment: (sample group, output-row tile) pair + a range of k blocks ---------------------------------
   int pair, part, cnt;
@@ -125,7 +128,12 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = ctl.tmem_base;
-  pdl_wait();              // everything above is local; from here on global memory of earlier kernels is read
+  stamp(tl, 1);
+  // Programmatic dependent launch: everything up to here is local.  mu and rho are written by the optimiser only, which
+  // completed before the previous kernel of the chain passed ITS wait, so the producer requests the first stages'
+  // parameter tiles before waiting; activations (and everything else) are touched after pdl_wait().
+  if (wid != 0) pdl_wait();
+  stamp(tl, 2);
 
   float lp[SG], lq[SG];
 #pragma unroll
@@ -135,18 +143,30 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
     // ================================ TMA producer ====================================================================
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)((1 + (need_rho ? 1 : 0) + nx) * TILE);
+      const int n_pre = min(NS, kb1 - kb0);
+      for (int it = 0; it < n_pre; ++it) {              // parameter tiles of the first stages: before the wait
+        const uint32_t sb = smem_u32(tiles + it * Cfg::kStage), bar = smem_u32(&ctl.full_in[it]);
+        tma::arrive_expect_tx(bar, bytes);
+        tma::load_2d(sb, &tm_mu, bar, (kb0 + it) * 32, o0);
+        if (need_rho) tma::load_2d(sb + TILE, &tm_rho, bar, (kb0 + it) * 32, o0);
+      }
+      pdl_wait();
       int it = 0;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int stage = it % NS;
-        if (it >= NS) mbar_wait(smem_u32(&ctl.empty[stage]), (uint32_t)(((it / NS) - 1) & 1));
         const uint32_t sb = smem_u32(tiles + stage * Cfg::kStage), bar = smem_u32(&ctl.full_in[stage]);
-        tma::arrive_expect_tx(bar, bytes);
-        tma::load_2d(sb, &tm_mu, bar, kb * 32, o0);
-        if (need_rho) tma::load_2d(sb + TILE, &tm_rho, bar, kb * 32, o0);
+        if (it >= NS) {
+          mbar_wait(smem_u32(&ctl.empty[stage]), (uint32_t)(((it / NS) - 1) & 1));
+          tma::arrive_expect_tx(bar, bytes);
+          tma::load_2d(sb, &tm_mu, bar, kb * 32, o0);
+          if (need_rho) tma::load_2d(sb + TILE, &tm_rho, bar, kb * 32, o0);
+        }
 #pragma unroll
         for (int s = 0; s < SG; ++s)
           if (s < nx) tma::load_3d(sb + (2 + s) * TILE, &tm_x, bar, kb * 32, 0, a.x_shared ? 0 : s0 + s);
       }
+    } else {
+      pdl_wait();
     }
     __syncwarp();
     pdl_launch_dependents();
@@ -201,12 +221,28 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
       bias_s[s][o_l] = bv;
     }
     const uint32_t tiles_u32 = smem_u32(tiles);
+    const bool relu_in = a.flags & BBB_F_RELU_IN;
     int it = 0;
     for (int kb = kb0; kb < kb1; ++kb, ++it) {
       const int stage = it % NS;
       mbar_wait(smem_u32(&ctl.full_in[stage]), (uint32_t)((it / NS) & 1));
+      if (it < 4) stamp(tl, 3 + 2 * it);
       const uint32_t sb = tiles_u32 + (uint32_t)(stage * Cfg::kStage);
       const bool col_ok = kb * 32 + c * 4 < a.in;
+      if (relu_in) {
+        // the activation tiles hold the producer's PRE-activation: max(., 0) in place (elementwise, so the swizzle
+        // does not matter: thread t owns bytes [16 t, 16 t + 16) of each 8 KB half of a tile)
+#pragma unroll
+        for (int s = 0; s < SG; ++s) {
+          if (s >= nx) break;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t ad = sb + (2 + s) * TILE + (uint32_t)(st * 16 + h * 8192);
+            const float4 v = lds128(ad);
+            sts128(ad, fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+          }
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         if (!row_ok[j]) {               // rows of the next tile: zero weights, so their accumulator lanes hold exact zeros
@@ -248,6 +284,7 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(smem_u32(&ctl.full_w[stage]));
+      if (it < 4) stamp(tl, 4 + 2 * it);
     }
     pdl_launch_dependents();
 
@@ -259,34 +296,37 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
     // tile's rows hold exact zeros (zero weight rows above).
     mbar_wait(smem_u32(&ctl.acc_full), 0u);
     tc_fence_after_sync();
+    stamp(tl, 11);
     {
       const int q = wid & 3, cg = (wid - 2) >> 2;          // TMEM lane quarter of this warp, 32-column group
       const uint32_t srow = tiles_u32 + (uint32_t)((q * 32 + lane) * 4 + cg * 32 * 512);
 #pragma unroll
       for (int s = 0; s < SG; ++s) {
         if (s >= ns) break;
+        const float bv = part == 0 ? bias_s[s][q * 32 + lane] : 0.0f;     // the pair's first CTA carries the bias
 #pragma unroll
         for (int cb = 0; cb < 32; cb += 16) {
           float v[16];
           tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128 + cg * 32 + cb), v);
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj)
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(srow + (uint32_t)(s * Cfg::kStage + (cb + jj) * 512)), "f"(v[jj]) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(srow + (uint32_t)(s * Cfg::kStage + (cb + jj) * 512)), "f"(v[jj] + bv) : "memory");
         }
       }
     }
     tc_fence_before_sync();
     fence_proxy_async_smem();
     bar_samplers();
+    stamp(tl, 12);
     if (st == 0) {
 #pragma unroll
       for (int s = 0; s < SG; ++s)
         if (s < ns) tma::reduce_add_3d(&tm_y, tiles_u32 + (uint32_t)(s * Cfg::kStage), o0, 0, s0 + s);
       tma::bulk_commit();
-      tma::bulk_wait_all();         // the adds are performed: the counter below may announce them
     }
+    stamp(tl, 13);
     tc_fence_before_sync();
-    // ---- log-prob sums of this CTA: warp sums -> one fp64 atomic per value (before the wait below: off the tail) ------
+    // ---- log-prob sums of this CTA: warp sums -> one fp64 atomic per value (while the reduce-add is in flight) --------
     if (kLogProb) {
       const int sw = wid - 2;
 #pragma unroll
@@ -294,62 +334,20 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         const float p = warp_sum(lp[s]), q2 = warp_sum(lq[s]);
         if (lane == 0) { red[(2 * s) * kSamplerWarps + sw] = p; red[(2 * s + 1) * kSamplerWarps + sw] = q2; }
       }
-    }
-    // ---- completion: every CTA of the pair bumps the pair's counter once its partial tile is in memory, waits until all
-    // of them have (the grid is at most one CTA per SM, so all CTAs are co-resident), and finalises ITS slice of the
-    // tile's batch rows: bias + optional ReLU -> the activation.  The finalisation is spread over the pair's CTAs
-    // instead of being the serial tail of the CTA that happens to arrive last.
-    __threadfence();
-    bar_samplers();
-    if (kLogProb && st < 2 * SG) {
-      const int s = st >> 1, which = st & 1;
-      if (s < ns) {
-        double v = 0.0;
+      bar_samplers();
+      if (st >= 32 && st < 32 + 2 * SG) {
+        const int s = (st - 32) >> 1, which = st & 1;
+        if (s < ns) {
+          double v = 0.0;
 #pragma unroll
-        for (int w8 = 0; w8 < kSamplerWarps; ++w8) v += (double)red[(2 * s + which) * kSamplerWarps + w8];
-        atomicAdd((which ? a.logq : a.logp) + s0 + s, v);
-      }
-    }
-    if (st == 0) {
-      atomicAdd(a.counters + pair, 1u);
-      uint32_t seen = 0;
-      for (int spin = 0; spin < (1 << 24); ++spin) {     // (bounded: a lost CTA must not hang the GPU)
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counters + pair) : "memory");
-        if (seen >= (uint32_t)cnt) break;
-        __nanosleep(64);
-      }
-    }
-    bar_samplers();
-    {
-      const int b_lo = (int)((int64_t)part * a.B / cnt), b_hi = (int)((int64_t)(part + 1) * a.B / cnt);
-      const int nq = rows >> 2, qd = st & 31;
-      const bool relu = a.flags & BBB_F_RELU_OUT;
-      if (qd < nq) {
-#pragma unroll
-        for (int s = 0; s < SG; ++s) {
-          if (s >= ns) break;
-          const float4 bq = *reinterpret_cast<const float4 *>(&bias_s[s][qd * 4]);
-          for (int bb = b_lo + (st >> 5); bb < b_hi; bb += 16 * 8) {
-            // all loads first (they are independent), then the stores: one L2 round trip
-            const int64_t off0 = ((int64_t)(s0 + s) * a.B + bb) * a.out + o0 + qd * 4;
-            float4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (bb + 16 * i < b_hi) v[i] = __ldcg(reinterpret_cast<const float4 *>(a.y_pre + off0 + (int64_t)(16 * i) * a.out));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (bb + 16 * i < b_hi) {
-                float4 t = v[i];
-                t.x += bq.x; t.y += bq.y; t.z += bq.z; t.w += bq.w;
-                if (relu) t = tcx::relu4(t);
-                *reinterpret_cast<float4 *>(a.act + off0 + (int64_t)(16 * i) * a.out) = t;
-              }
-            }
-          }
+          for (int w8 = 0; w8 < kSamplerWarps; ++w8) v += (double)red[(2 * s + which) * kSamplerWarps + w8];
+          atomicAdd((which ? a.logq : a.logp) + s0 + s, v);
         }
       }
     }
+    if (st == 0) tma::bulk_wait_all();      // the partial tile has been added to the output (and its staging read)
   }
+  stamp(tl, 15);
   tc_fence_before_sync();
   __syncthreads();
   if (wid == 1) tmem_dealloc(tmem, Cfg::kTmemCols);
@@ -378,20 +376,20 @@ inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 bool mlp_fwd_layer_supported(const MlpLayerDesc &l, int64_t S, int64_t B) {
   if (!(B >= 1 && B <= 128 && S >= 1 && l.in >= 4 && l.in % 4 == 0 && l.out >= 4 && l.out % 4 == 0)) return false;
-  if (!(al16(l.x) && al16(l.w_mu) && al16(l.w_rho) && al16(l.eps_w) && al16(l.y_pre) && al16(l.act))) return false;
+  if (!(al16(l.x) && al16(l.w_mu) && al16(l.w_rho) && al16(l.eps_w) && al16(l.y))) return false;
   const int n_ot = cdiv_i(l.out, 128), groups = cdiv_i(S, 2);
   return (int64_t)n_ot * groups <= sm_count() && l.in * l.out / 4 < (int64_t)1 << 32;
 }
 
-// One layer: x [Sx,B,in] (x_shared: [B,in]) -> act [S,B,out] = (relu)(x W_s^T + b_s), log-prob sums added to logp/logq.
-// y_pre [S,B,out] and counters [groups * n_ot] must be zero-filled.
+// One layer: x [Sx,B,in] (x_shared: [B,in]; BBB_F_RELU_IN: max(x, 0) is applied to the loaded tiles) -> y [S,B,out] +=
+// x W_s^T + b_s (y must be zero-filled), log-prob sums added to logp / logq.
 int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngDev &rng, const PriorDev &prior, int flags,
                          double *logp, double *logq, cudaStream_t st) {
   const bool sample = flags & BBB_F_SAMPLE, lpq = flags & BBB_F_LOGPROB;
   const int mode = !sample ? 2 : (l.eps_w ? 1 : 0);
   MlpFwdArgs a{};
   a.b_mu = l.b_mu; a.b_rho = l.b_rho; a.eps_w = l.eps_w; a.eps_b = l.eps_b;
-  a.y_pre = l.y_pre; a.act = l.act; a.counters = l.counters; a.logp = logp; a.logq = logq;
+  a.logp = logp; a.logq = logq;
   a.rng = rng; a.prior = prior;
   a.S = (int)S; a.B = (int)B; a.in = (int)l.in; a.out = (int)l.out; a.in4 = (int)(l.in / 4);
   a.n_ot = cdiv_i(l.out, 128);
@@ -399,6 +397,7 @@ int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngD
   a.n_ot = cdiv_i(l.out, a.T_o);
   a.nkb = cdiv_i(l.in, 32);
   a.flags = flags; a.x_shared = l.x_shared ? 1 : 0;
+  a.timeline = debug_timeline();
   const int sg = S >= 2 ? 2 : 1, groups = cdiv_i(S, sg), pairs = groups * a.n_ot;
   int grid = sm_count();
   if ((int64_t)pairs * a.nkb < grid) grid = pairs * a.nkb;
@@ -409,7 +408,7 @@ int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngD
   if (l.w_rho)
     if (int r = tma::make_map(&tm[1], l.w_rho, l.in, l.out, 0, 32, 128, tma::kNone)) return r;
   if (int r = tma::make_map(&tm[2], l.x, l.in, B, l.x_shared ? 1 : S, 32, 128, tma::kSw128)) return r;
-  if (int r = tma::make_map(&tm[3], l.y_pre, l.out, B, S, 128, 128, tma::kNone)) return r;   // split-K reduce-add target
+  if (int r = tma::make_map(&tm[3], l.y, l.out, B, S, 128, 128, tma::kNone)) return r;   // split-K reduce-add target
   return sg == 2 ? launch_sg<2>(tm, a, grid, mode, lpq, st) : launch_sg<1>(tm, a, grid, mode, lpq, st);
 }
 

@@ -418,51 +418,41 @@ def _layerwise_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, n
     return ys, dxs, d_out
 
 
-def _mlp_layer_table(params, eps, ypre, acts, counters, dzs, grads):
+def _mlp_layer_table(params, eps, ys, dzs, grads):
     tab = (L.MlpLayer * len(params))()
     for l, p in enumerate(params):
         t = tab[l]
         t.w_mu, t.w_rho, t.b_mu, t.b_rho = (q.data_ptr() for q in p)
         t.eps_w, t.eps_b = eps.ptrs(l)
         t.out, t.inn = p[0].shape
-        t.y_pre, t.act = L.ptr(ypre[l]), L.ptr(acts[l])
-        t.counters, t.dz = L.ptr(counters[l]), L.ptr(dzs[l])
+        t.y, t.dz = L.ptr(ys[l]), L.ptr(dzs[l])
         if grads is not None:
             t.g_w_mu, t.g_w_rho, t.g_b_mu, t.g_b_rho = (g.data_ptr() for g in grads[l])
     return tab
 
 
 def _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, beta_h, beta_d, out4):
-    """sample_elbo's forward as ONE C call (bbb_mlp_fwd): TMA-fed tcgen05 kernels for the hidden layers, whose outputs
-    are stored as ACTIVATIONS (post-ReLU), + the fused head.  Returns (acts, dxs, d_out) with acts[l] the post-ReLU
-    output of hidden layer l (max(., 0) is idempotent and (relu(y) > 0) == (y > 0), so the backward can take them where
-    it took the pre-activations) and dxs[l] the zero-filled gradient buffer w.r.t. layer l's pre-activation input."""
+    """sample_elbo's forward as ONE C call (bbb_mlp_fwd): TMA-fed tcgen05 kernels for the hidden layers + the fused
+    head.  Returns (ys, dxs, d_out): ys[l] the pre-activation output of layer l (the hidden ones live in the zero-filled
+    workspace: their split-K partial tiles are reduce-added into it), dxs[l] the zero-filled gradient buffer w.r.t.
+    layer l's pre-activation input."""
     dev = x2.device
     nl = len(params)
-    groups = (S + 1) // 2
     hidden = [p[0].shape[0] for p in params[:-1]]
-    n_cnt = [groups * ((h + 127) // 128) for h in hidden]
-    # zero-filled (one memset): fp64 accumulators, done counter, tile counters | split-K scratch of every hidden layer |
+    # zero-filled (one memset): fp64 accumulators + the head's done counter | pre-activations of every hidden layer |
     # gradient w.r.t. every hidden layer's pre-activation output (the layer above adds its partial dx tiles into it)
-    shapes = [(2 * (2 * S + 1) + 2 + sum(n_cnt),)] + [(S, B, h) for h in hidden]
+    shapes = [(2 * (2 * S + 1) + 2,)] + [(S, B, h) for h in hidden]
     if need_grad:
         shapes += [(S, B, h) for h in hidden]
     ws = _zeroed_views(shapes, dev)
-    head = ws[0]
-    acc = head[:2 * (2 * S + 1)].view(torch.float64)
-    done = head[2 * (2 * S + 1):2 * (2 * S + 1) + 2]
-    counters, off = [], 2 * (2 * S + 1) + 2
-    for n in n_cnt:
-        counters.append(head[off:off + n])
-        off += n
-    counters.append(None)
-    ypre = ws[1:1 + len(hidden)] + [None]
+    acc = ws[0][:2 * (2 * S + 1)].view(torch.float64)
+    done = ws[0][2 * (2 * S + 1):]
+    Cc = params[-1][0].shape[0]
+    ys = ws[1:1 + len(hidden)] + [torch.empty((S, B, Cc), dtype=torch.float32, device=dev)]
     dzs = (ws[1 + len(hidden):] if need_grad else [None] * len(hidden))
     logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
-    acts = [torch.empty((S, B, p[0].shape[0]), dtype=torch.float32, device=dev) for p in params]
-    Cc = params[-1][0].shape[0]
     d_out = torch.empty((S, B, Cc), dtype=torch.float32, device=dev) if need_grad else None
-    tab = _mlp_layer_table(params, eps, ypre, acts, counters, list(dzs) + [d_out], None)
+    tab = _mlp_layer_table(params, eps, ys, list(dzs) + [d_out], None)
     kind = L.NLL_CE if mode == 'classification' else L.NLL_GAUSS
     tgt = target if mode == 'classification' else _f32c(target)
     rng = eps.rng(0)
@@ -470,7 +460,7 @@ def _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_gr
                                 L.F_SAMPLE | L.F_LOGPROB | L.F_TF32, kind, L.ptr(tgt), float(sigma), 1.0 / S,
                                 L.ptr(d_out), L.ptr(logp), L.ptr(logq), L.ptr(nll), beta_h, L.ptr(beta_d), L.ptr(out4),
                                 L.ptr(done), L.stream()), 'bbb_mlp_fwd')
-    return acts, ([None] + list(dzs) if need_grad else None), d_out
+    return ys, ([None] + list(dzs) if need_grad else None), d_out
 
 
 class _FusedELBO(torch.autograd.Function):
@@ -532,12 +522,12 @@ class _FusedELBO(torch.autograd.Function):
                                  scale, False, ctx.fused_opt, ctx.live, ctx.dxs)
             return (None,) * (9 + 4 * nl)
         if ctx.used_mlp:
-            # ONE C call for the whole backward (bbb_mlp_bwd): ys are the stored activations, ctx.dxs[l + 1] the
+            # ONE C call for the whole backward (bbb_mlp_bwd): ys are the stored pre-activations, ctx.dxs[l + 1] the
             # zero-filled gradient w.r.t. hidden layer l's pre-activation output
             grads = _alloc_grads(params)
             B = x2.shape[0]
             dzs = list(ctx.dxs[1:]) + [d_out]
-            tab = _mlp_layer_table(params, eps, [None] * nl, ys, [None] * nl, dzs, grads)
+            tab = _mlp_layer_table(params, eps, ys, dzs, grads)
             rng = eps.rng(0)
             L.check(L.lib().bbb_mlp_bwd(tab, nl, L.ptr(x2), S, B, C.byref(rng), C.byref(prior), L.F_SAMPLE | L.F_TF32,
                                         -beta / S, beta / S, L.ptr(bd), L.ptr(bd), 0, L.ptr(scale), L.stream()),

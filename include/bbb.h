@@ -53,7 +53,6 @@ extern "C" {
 #define BBB_F_NO_WGRAD 128 /* backward: do not compute parameter gradients (dx only)           */
 #define BBB_F_DX_PREACT 512 /* backward, with BBB_F_RELU_IN: dx is multiplied by (x > 0), i.e. it is the gradient
                               w.r.t. the PRE-activation input; the layer below then needs no dy_mask_src      */
-#define BBB_F_RELU_OUT 1024 /* network-level forward (bbb_mlp_fwd): the layer stores max(y, 0), the ACTIVATION its consumer loads */
 #define BBB_F_OUT_ZEROED 256 /* y (forward) / dx (backward) is already zero-filled by the caller: kernels that
                                combine split-K partial sums with red.add skip their own memset              */
 
@@ -203,16 +202,14 @@ int bbb_head_fwd(const float *x, int64_t x_sample_stride, const float *w_mu, con
 
 /* ---- the whole network in one call (batches of at most 128 rows, tcgen05 kind::tf32) ---------------------------------
  * bbb_mlp_fwd = the body of BayesianNetwork.sample_elbo (networks.py:192-209): BayesianNetwork.forward (166-172) for
- * all S samples -- every hidden BayesianLinear.forward (73-88) followed by ReLU -- then the head as bbb_head_fwd does
- * it (last layer + get_nll (183-190) and its gradient + the four returned scalars).  Replaces n_layers calls of
- * bbb_linear_fwd / bbb_head_fwd: one host call per network pass, and a different data flow between the layers: a
- * hidden layer's output is stored as the ACTIVATION max(x W_s^T + b_s, 0) (its split-K partial tiles are added into
- * the zero-filled y_pre scratch and the CTA that completes a tile finalises it), so that the next layer -- and the
- * backward -- load it with TMA exactly as it lies.
+ * all S samples -- every hidden BayesianLinear.forward (73-88); the ReLU between layers is applied by the CONSUMER, in
+ * shared memory, to the tile its TMA has loaded -- then the head as bbb_head_fwd does it (last layer + get_nll (183-190)
+ * and its gradient + the four returned scalars).  Replaces n_layers calls of bbb_linear_fwd / bbb_head_fwd: one host call
+ * per network pass.
  *   layers[l]  w_mu, w_rho [out,in]; b_mu, b_rho [out]; eps_w [S,out,in] / eps_b [S,out] or NULL (Philox, tensor ids
  *              2l / 2l+1: rng->layer is ignored);  in of layer l+1 == out of layer l
- *              y_pre [S,B,out] zero-filled scratch and counters (cdiv(S,2) * cdiv(out,128) zero-filled words): hidden layers
- *              act   [S,B,out] written: hidden layers the activation, last layer the network's outputs
+ *              y [S,B,out]: the layer's PRE-activation output x W_s^T + b_s.  Hidden layers: must be ZERO-FILLED (the
+ *              split-K partial tiles are added into it with TMA reduce-add); last layer: written
  *              dz, g_*: backward only (bbb_mlp_bwd)
  *   x [B,in0] is shared by all samples;  nll_kind / target / sigma / grad_scale / d_out / nll / beta / beta_dev / out4 /
  *   done_counter exactly as in bbb_head_fwd (d_out [S,B,out_last] = grad_scale * d nll / d outputs).
@@ -222,8 +219,7 @@ int bbb_head_fwd(const float *x, int64_t x_sample_stride, const float *w_mu, con
 typedef struct bbb_mlp_layer {
   const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_w, *eps_b;
   int64_t in, out;
-  float *y_pre, *act;
-  uint32_t *counters;
+  float *y;                                       /* [S,B,out] pre-activation output (hidden layers: zero-filled)          */
   float *dz;                                      /* [S,B,out]: hidden layers zero-filled, accumulated by the layer above */
   float *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;     /* parameter gradients, overwritten                                     */
 } bbb_mlp_layer;
@@ -234,9 +230,9 @@ int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, i
                 const float *beta_dev, float *out4, uint32_t *done_counter, void *stream);
 /* bbb_mlp_bwd = the autograd backward of the above (triggered at reg_task.py:72, class_task.py:78, bandits.py:49), all
  * layers in one call; replaces n_layers calls of bbb_linear_bwd (same gp / gq / gp_dev / gq_dev / g_dev_stride /
- * out_scale_dev meaning, eps regenerated from the same Philox coordinates).  Reads layers[l].act (the activations the
+ * out_scale_dev meaning, eps regenerated from the same Philox coordinates).  Reads layers[l].y (the pre-activations the
  * forward stored) and layers[n-1].dz (= d_out of bbb_mlp_fwd); layers[l].dz of the hidden layers must be zero-filled:
- * the layer above adds (dz W_s) (act > 0) into it.  Writes g_w_mu / g_w_rho / g_b_mu / g_b_rho of every layer
+ * the layer above adds (dz W_s) (y > 0) into it.  Writes g_w_mu / g_w_rho / g_b_mu / g_b_rho of every layer
  * (added to with BBB_F_ACCUM). */
 int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, int64_t S, int64_t B,
                 const bbb_rng *rng, const bbb_prior *prior, int32_t flags, float gp, float gq, const float *gp_dev,
@@ -295,6 +291,10 @@ int bbb_adam_step_peer(const bbb_peer_comm *comm, float *exp_avg, float *exp_avg
  * on the launching stream (do not enable while a CUDA graph is being captured); bbb_timing_report synchronises the
  * device and writes a JSON object {"kernel[inxout]": [total ms, launches], ...} into buf (HOST pointer). */
 int bbb_timing_enable(int32_t on);
+/* debug aid: when buf != NULL every CTA of the network-level kernels launched afterwards writes 16 %globaltimer stamps
+ * (phase boundaries, ns) at buf[2560 * launch + 16 * cta ..] (launch = 0..7, in launch order; buf holds 8 * 2560 words);
+ * tools/kernel_timeline.py prints the phase durations.  NULL switches it off. */
+int bbb_debug_set_timeline(unsigned long long *buf);
 int bbb_timing_report(char *buf, int64_t buf_bytes);
 
 /* *counter += inc  (advances a bbb_rng.step_dev between steps; one tiny launch, graph-capturable) */

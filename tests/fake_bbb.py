@@ -14,7 +14,7 @@ import numpy as np
 from oracle import closed_form as CF
 
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
-F_OUT_ZEROED, F_DX_PREACT, F_RELU_OUT = 256, 512, 1024
+F_OUT_ZEROED, F_DX_PREACT = 256, 512
 
 
 def _arr(ptr, ctype, *shape):
@@ -295,36 +295,33 @@ class FakeLib:
 
     def bbb_mlp_fwd(self, layers, n_layers, x, S, B, rng, prior, flags, nll_kind, target, sigma, scale, d_out, logp, logq,
                     nll, beta, beta_dev, out4, done, st):
-        """hidden layers: act = relu(x W_s^T + b_s) (y_pre / counters are kernel scratch and must arrive zeroed);
-        last layer: bbb_head_fwd on the last activation"""
+        """hidden layers: y = x W_s^T + b_s ADDED into the zero-filled pre-activation buffer, ReLU applied by the consumer;
+        last layer: bbb_head_fwd on the last pre-activation"""
         self.calls.append('mlp_fwd')
         n0 = len(self.calls)
         inp, xs = x, 0
         for l in range(n_layers - 1):
             t = layers[l]
-            assert t.y_pre and t.counters and t.act, 'fake lib: hidden layers need y_pre, counters and act'
-            assert not np.any(_f(t.y_pre, S, B, t.out)) and _arr(t.counters, C.c_uint32, 1)[0] == 0, 'scratch must be zeroed'
+            assert t.y and not np.any(_f(t.y, S, B, t.out)), 'fake lib: hidden pre-activation buffers must arrive zeroed'
             self.bbb_linear_fwd(inp, xs, t.w_mu, t.w_rho, t.b_mu, t.b_rho, t.eps_w, t.eps_b, rng, prior, S, B, t.inn,
-                                t.out, flags & (F_SAMPLE | F_LOGPROB), t.act, logp, logq, st)
-            A = _f(t.act, S, B, t.out)
-            A[...] = np.maximum(A, 0)
-            inp, xs = t.act, B * t.out
+                                t.out, (flags & (F_SAMPLE | F_LOGPROB)) | (F_RELU_IN if l > 0 else 0), t.y, logp, logq, st)
+            inp, xs = t.y, B * t.out
         t = layers[n_layers - 1]
         self.bbb_head_fwd(inp, xs, t.w_mu, t.w_rho, t.b_mu, t.b_rho, t.eps_w, t.eps_b, rng, prior, S, B, t.inn, t.out,
-                          flags & (F_SAMPLE | F_LOGPROB), nll_kind, target, sigma, scale, t.act, d_out, logp, logq, nll,
-                          beta, beta_dev, out4, done, st)
+                          (flags & (F_SAMPLE | F_LOGPROB)) | F_RELU_IN, nll_kind, target, sigma, scale, t.y, d_out, logp,
+                          logq, nll, beta, beta_dev, out4, done, st)
         del self.calls[n0:]
         self.calls.append('head_fwd')
         return 0
 
     def bbb_mlp_bwd(self, layers, n_layers, x, S, B, rng, prior, flags, gp, gq, gp_dev, gq_dev, gstride, oscale, st):
-        """backward of bbb_mlp_fwd: per layer bbb_linear_bwd on the stored activations; the gradient w.r.t. a hidden
+        """backward of bbb_mlp_fwd: per layer bbb_linear_bwd on the stored pre-activations; the gradient w.r.t. a hidden
         layer's pre-activation output is ADDED into its (zero-filled) dz buffer"""
         self.calls.append('mlp_bwd')
         n0 = len(self.calls)
         for l in reversed(range(n_layers)):
             t = layers[l]
-            inp, xs = (layers[l - 1].act, B * t.inn) if l > 0 else (x, 0)
+            inp, xs = (layers[l - 1].y, B * t.inn) if l > 0 else (x, 0)
             fl = (flags & (F_SAMPLE | F_ACCUM)) | ((F_RELU_IN | F_DX_PREACT) if l > 0 else F_NO_DX)
             dx = None
             if l > 0:
@@ -383,6 +380,9 @@ class FakeLib:
         return 0
 
     def bbb_timing_enable(self, on):
+        return 0
+
+    def bbb_debug_set_timeline(self, buf):
         return 0
 
     def bbb_timing_report(self, buf, n):
