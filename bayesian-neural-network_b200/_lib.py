@@ -67,7 +67,7 @@ _SIGS = {
                       P, P, P, P], C.c_int),
     'bbb_mlp_supported': ([P, I32, I64, I64, I32], C.c_int),
     'bbb_mlp_fwd': ([P, I32, P, I64, I64, P, P, I32, I32, P, F32, F32, P, P, P, P, F32, P, P, P, P], C.c_int),
-    'bbb_mlp_bwd': ([P, I32, P, I64, I64, P, P, I32, F32, F32, P, P, I64, P, P], C.c_int),
+    'bbb_mlp_bwd': ([P, I32, P, I64, I64, P, P, I32, F32, F32, P, P, I64, P, P, P], C.c_int),
     'bbb_elbo_finalize': ([P, P, P, P, I64, F32, P, P, P], C.c_int),
     'bbb_adam_step': ([I32, P, P, P, P, P, F64, F64, F64, F64, U32, P, P, P], C.c_int),
     'bbb_enable_peer_access': ([I32], C.c_int),

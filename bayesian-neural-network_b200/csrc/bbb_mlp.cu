@@ -200,8 +200,10 @@ extern "C" int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
 extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, int64_t S, int64_t B,
                            const bbb_rng *rng, const bbb_prior *prior, int32_t flags, float gp, float gq,
                            const float *gp_dev, const float *gq_dev, int64_t g_dev_stride, const float *out_scale_dev,
-                           void *stream) {
+                           const bbb_adam_fuse *adam, void *stream) {
   BBB_CHECK_ARG(layers && x && n_layers >= 2 && n_layers <= 64, "null pointer or bad layer count");
+  if (adam && (S > 2 || (flags & BBB_F_ACCUM)))
+    return fail(BBB_EUNSUPPORTED, "bbb_mlp_bwd: the fused optimiser needs S <= 2 (one sample group) and no BBB_F_ACCUM");
   BBB_CHECK_ARG(flags & BBB_F_TF32, "the network-level kernels are the tcgen05 kind::tf32 path: pass BBB_F_TF32");
   BBB_CHECK_ARG(g_dev_stride == 0 || g_dev_stride == 1, "g_dev_stride must be 0 or 1");
   BBB_CHECK_ARG(((gp == 0.0f) && !gp_dev) || prior, "prior required when gp != 0");
@@ -210,8 +212,11 @@ extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
   dims[0] = layers[0].in;
   for (int l = 0; l < n_layers; ++l) {
     const bbb_mlp_layer &L = layers[l];
-    BBB_CHECK_ARG(L.w_mu && L.w_rho && L.b_mu && L.b_rho && L.dz && L.g_w_mu && L.g_w_rho && L.g_b_mu && L.g_b_rho,
-                  "null layer pointer");
+    BBB_CHECK_ARG(L.w_mu && L.w_rho && L.b_mu && L.b_rho && L.dz, "null layer pointer");
+    // (with the fused optimiser only the head still writes its gradients: its update is a separate small launch)
+    BBB_CHECK_ARG((adam && l + 1 < n_layers) || (L.g_w_mu && L.g_w_rho && L.g_b_mu && L.g_b_rho), "null gradient pointer");
+    if (adam)
+      for (int k = 0; k < 4; ++k) BBB_CHECK_ARG(adam[l].exp_avg[k] && adam[l].exp_avg_sq[k], "null optimiser state");
     BBB_CHECK_ARG(!sample || (L.eps_w && L.eps_b) || (!L.eps_w && !L.eps_b && rng), "give both eps pointers or an rng");
     BBB_CHECK_ARG(L.in == dims[l], "layer widths do not chain");
     BBB_CHECK_ARG(l + 1 == n_layers || L.y, "hidden layers need their stored pre-activation");
@@ -245,8 +250,18 @@ extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
       return fail(BBB_EUNSUPPORTED, "bbb_mlp_bwd: layer %d needs 16-byte aligned tensors", l);
     ScopedTimer tm("mlp_bwd[%lldx%lld]", (long long)d.in, (long long)d.out, st);
     if (int rc = launch_mlp_bwd_layer(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, keep | (l > 0 ? BBB_F_RELU_IN : 0), gp, gq, gp_dev, gq_dev,
-                                      (int)g_dev_stride, out_scale_dev, st))
+                                      (int)g_dev_stride, out_scale_dev, adam ? &adam[l] : nullptr, st))
       return rc;
+  }
+  if (adam) {      // the head's few thousand parameters: the stand-alone multi-tensor update on the gradients it wrote
+    const bbb_mlp_layer &H = layers[n_layers - 1];
+    const bbb_adam_fuse &A = adam[n_layers - 1];
+    float *params[4] = {const_cast<float *>(H.w_mu), const_cast<float *>(H.w_rho), const_cast<float *>(H.b_mu), const_cast<float *>(H.b_rho)};
+    const float *grads[4] = {H.g_w_mu, H.g_w_rho, H.g_b_mu, H.g_b_rho};
+    const int64_t sizes[4] = {H.in * H.out, H.in * H.out, H.out, H.out};
+    ScopedTimer tm("head_adam[%lldx%lld]", (long long)H.in, (long long)H.out, st);
+    return bbb_adam_step(4, params, grads, A.exp_avg, A.exp_avg_sq, sizes, A.lr, A.beta1, A.beta2, A.eps, A.step, A.step_dev,
+                         A.lr_scale_dev, stream);
   }
   return BBB_OK;
 }

@@ -45,6 +45,14 @@ struct MlpBwdArgs {
   const float *gp_dev, *gq_dev, *out_scale_dev;   // ... times optional device scalars (bbb_linear_bwd semantics)
   int g_dev_stride;
   unsigned long long *timeline;   // debug: 16 globaltimer stamps per CTA, or NULL
+  // optional optimiser step fused into the gradient write-back (bbb_mlp_bwd with an Adam descriptor, S <= 2): state of
+  // w_mu, w_rho, b_mu, b_rho; the parameters are updated in place and no gradient is written
+  float *adam_m[4], *adam_v[4];
+  double adam_lr, adam_b1, adam_b2;
+  float adam_eps;
+  uint32_t adam_step;
+  const uint32_t *adam_step_dev;
+  const float *adam_lr_scale_dev;
 };
 
 // debug: phase time stamps of the network-level kernels (tools/kernel_timeline.py)
@@ -63,6 +71,6 @@ int launch_mlp_fwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngD
 bool mlp_bwd_layer_supported(const MlpLayerDesc &l, int64_t S, int64_t B);
 int launch_mlp_bwd_layer(const MlpLayerDesc &l, int64_t S, int64_t B, const RngDev &rng, const PriorDev &prior, int flags,
                          float gp, float gq, const float *gp_dev, const float *gq_dev, int g_dev_stride,
-                         const float *out_scale_dev, cudaStream_t st);
+                         const float *out_scale_dev, const bbb_adam_fuse *adam, cudaStream_t st);
 
 }  // namespace bbb

@@ -426,7 +426,7 @@ def _mlp_layer_table(params, eps, ys, dzs, grads):
         t.eps_w, t.eps_b = eps.ptrs(l)
         t.out, t.inn = p[0].shape
         t.y, t.dz = L.ptr(ys[l]), L.ptr(dzs[l])
-        if grads is not None:
+        if grads is not None and grads[l] is not None:
             t.g_w_mu, t.g_w_rho, t.g_b_mu, t.g_b_rho = (g.data_ptr() for g in grads[l])
     return tab
 
@@ -480,8 +480,9 @@ class _FusedELBO(torch.autograd.Function):
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
         beta_h, beta_d = _split_beta(beta)
         dims = [params[0][0].shape[1]] + [p[0].shape[0] for p in params]
-        use_mlp = (use_network_level_call and tf32 and fused_opt is None and mode in ('classification', 'regression') and
-                   L.mlp_supported(dims, S, B, L.F_TF32))
+        # (the optimiser fused into the network-level backward needs one sample group: S <= 2)
+        use_mlp = (use_network_level_call and tf32 and (fused_opt is None or S <= 2) and
+                   mode in ('classification', 'regression') and L.mlp_supported(dims, S, B, L.F_TF32))
         if use_mlp:
             ys, dxs, d_out = _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, beta_h,
                                                beta_d, out4)
@@ -516,6 +517,22 @@ class _FusedELBO(torch.autograd.Function):
         ys = list(sv[2 + 4 * nl:2 + 4 * nl + nl - 1]) + [None]
         scale = _f32c(g_loss).reshape(1)
         bd = ctx.beta_dev
+        if ctx.fused_opt is not None and ctx.used_mlp:
+            # ONE C call: backward of every layer with the optimiser's update applied in the kernels' gradient write-back
+            # (parameters change here, no .grad appears); only the head's gradients are materialised (scratch)
+            with torch.no_grad():
+                B = x2.shape[0]
+                hg = _alloc_grads(params[-1:])
+                tab = _mlp_layer_table(params, eps, ys, list(ctx.dxs[1:]) + [d_out], [None] * (nl - 1) + [hg[0]])
+                adam = (L.AdamFuse * nl)()
+                for l in range(nl):
+                    d = ctx.fused_opt.fuse_descriptor(ctx.live[l])
+                    C.memmove(C.byref(adam[l]), C.byref(d), C.sizeof(L.AdamFuse))
+                rng = eps.rng(0)
+                L.check(L.lib().bbb_mlp_bwd(tab, nl, L.ptr(x2), S, B, C.byref(rng), C.byref(prior),
+                                            L.F_SAMPLE | L.F_TF32, -beta / S, beta / S, L.ptr(bd), L.ptr(bd), 0,
+                                            L.ptr(scale), adam, L.stream()), 'bbb_mlp_bwd')
+            return (None,) * (9 + 4 * nl)
         if ctx.fused_opt is not None:     # Adam rides in the backward kernels: parameters change here, no .grad appears
             with torch.no_grad():
                 _net_ws_backward(x2, ys, d_out, params, prior, S, eps, True, tf32, -beta / S, beta / S, bd, bd, 0,
@@ -530,7 +547,7 @@ class _FusedELBO(torch.autograd.Function):
             tab = _mlp_layer_table(params, eps, ys, dzs, grads)
             rng = eps.rng(0)
             L.check(L.lib().bbb_mlp_bwd(tab, nl, L.ptr(x2), S, B, C.byref(rng), C.byref(prior), L.F_SAMPLE | L.F_TF32,
-                                        -beta / S, beta / S, L.ptr(bd), L.ptr(bd), 0, L.ptr(scale), L.stream()),
+                                        -beta / S, beta / S, L.ptr(bd), L.ptr(bd), 0, L.ptr(scale), None, L.stream()),
                     'bbb_mlp_bwd')
             if grad_ready_hook is not None:
                 for l in reversed(range(nl)):

@@ -51,6 +51,8 @@ def parse():
     ap.add_argument('--tf32', type=int, default=-1, help='1: tcgen05 kind::tf32 path, 0: exact fp32 FMA, -1: default')
     ap.add_argument('--eager', action='store_true', help='time the eager call sequence instead of the captured graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--fuse-opt', type=int, default=1,
+                    help='1 GPU: apply Adam inside the backward kernels (bbb_mlp_bwd with an Adam descriptor); 0: separate launch')
     ap.add_argument('--comm', default='peer', choices=['peer', 'nccl'],
                     help='N > 1: peer = gradient reduce-scatter + Adam + parameter all-gather in one kernel over NVLink '
                          'peer memory (PeerShardedAdam); nccl = per-layer NCCL all-reduce overlapped with the backward + FusedAdam')
@@ -376,7 +378,8 @@ def run_b200(args):
     graphed, graph_note = None, 'eager call sequence (--eager)'
     if not args.eager:
         try:
-            graphed = bnn_b200.GraphedTrainStep(net, opt, x_d, y_d, S, sigma=sigma, beta=beta, world_size=world)
+            graphed = bnn_b200.GraphedTrainStep(net, opt, x_d, y_d, S, sigma=sigma, beta=beta, world_size=world,
+                                                fuse_optimizer=bool(args.fuse_opt) and world == 1)
             graph_note = 'whole step captured in one CUDA graph (bnn_b200.GraphedTrainStep), one replay per step'
         except Exception as e:          # e.g. a collective that cannot be captured: fall back to the eager sequence
             graphed, graph_note = None, f'eager call sequence (graph capture failed: {type(e).__name__}: {e})'

@@ -233,10 +233,17 @@ int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, i
  * out_scale_dev meaning, eps regenerated from the same Philox coordinates).  Reads layers[l].y (the pre-activations the
  * forward stored) and layers[n-1].dz (= d_out of bbb_mlp_fwd); layers[l].dz of the hidden layers must be zero-filled:
  * the layer above adds (dz W_s) (y > 0) into it.  Writes g_w_mu / g_w_rho / g_b_mu / g_b_rho of every layer
- * (added to with BBB_F_ACCUM). */
+ * (added to with BBB_F_ACCUM).
+ * adam (nullable; n_layers descriptors, see bbb_linear_bwd_adam): the optimiser's next step is applied by the backward
+ * kernels themselves -- replaces loss.backward() + optimiser.step() (reg_task.py:72-73, class_task.py:78-79,
+ * bandits.py:49-50) for single-GPU steps with S <= 2: a hidden layer's CTA that holds the complete gradient of its block
+ * of weights updates w_mu / w_rho / b_mu / b_rho and the Adam state in place in its coalesced write-back and writes no
+ * gradient (g_* of hidden layers may be NULL); the head's gradients are written and updated by one small launch.
+ * sqrt and the division use the SFU approximations (1-ulp level).  Returns BBB_EUNSUPPORTED for S > 2 or BBB_F_ACCUM. */
 int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const float *x, int64_t S, int64_t B,
                 const bbb_rng *rng, const bbb_prior *prior, int32_t flags, float gp, float gq, const float *gp_dev,
-                const float *gq_dev, int64_t g_dev_stride, const float *out_scale_dev, void *stream);
+                const float *gq_dev, int64_t g_dev_stride, const float *out_scale_dev, const bbb_adam_fuse *adam,
+                void *stream);
 
 /* ELBO assembly (networks.py:205-209 / 221-225):
  * out4 = { beta mean(logq) - beta mean(logp) + nll/S, mean(logp), mean(logq), nll/S }   (kl == NULL)

@@ -314,7 +314,7 @@ class FakeLib:
         self.calls.append('head_fwd')
         return 0
 
-    def bbb_mlp_bwd(self, layers, n_layers, x, S, B, rng, prior, flags, gp, gq, gp_dev, gq_dev, gstride, oscale, st):
+    def bbb_mlp_bwd(self, layers, n_layers, x, S, B, rng, prior, flags, gp, gq, gp_dev, gq_dev, gstride, oscale, adam, st):
         """backward of bbb_mlp_fwd: per layer bbb_linear_bwd on the stored pre-activations; the gradient w.r.t. a hidden
         layer's pre-activation output is ADDED into its (zero-filled) dz buffer"""
         self.calls.append('mlp_bwd')
@@ -327,9 +327,26 @@ class FakeLib:
             if l > 0:
                 assert not np.any(_f(layers[l - 1].dz, S, B, t.inn)), 'fake lib: hidden dz buffers must be zeroed'
                 dx = layers[l - 1].dz
+            gptrs = (t.g_w_mu, t.g_w_rho, t.g_b_mu, t.g_b_rho)
+            shapes = ((t.out, t.inn), (t.out, t.inn), (t.out,), (t.out,))
+            if adam is not None:            # the optimiser's update replaces the gradient output (the head still writes its own)
+                assert S <= 2 and not flags & F_ACCUM
+                gs = [np.zeros(sh, dtype=np.float32) for sh in shapes]
+                if l + 1 < n_layers:
+                    gptrs = tuple(g.ctypes.data for g in gs)
             self.bbb_linear_bwd(t.dz, None, inp, xs, t.w_mu, t.w_rho, t.b_mu, t.b_rho, t.eps_w, t.eps_b, rng, prior, S, B,
-                                t.inn, t.out, fl, gp, gq, gp_dev, gq_dev, gstride, oscale, dx, t.g_w_mu, t.g_w_rho,
-                                t.g_b_mu, t.g_b_rho, st)
+                                t.inn, t.out, fl, gp, gq, gp_dev, gq_dev, gstride, oscale, dx, *gptrs, st)
+            if adam is not None:
+                d = adam[l]
+                step = d.step + (int(_arr(d.step_dev, C.c_uint32, 1)[0]) if d.step_dev else 0)
+                lr = d.lr * (float(_f(d.lr_scale_dev, 1)[0]) if d.lr_scale_dev else 1.0)
+                bc1, bc2 = 1 - d.beta1 ** step, 1 - d.beta2 ** step
+                for k, (ptr, sh) in enumerate(zip((t.w_mu, t.w_rho, t.b_mu, t.b_rho), shapes)):
+                    g = _f(gptrs[k], *sh)
+                    p, m, v = _f(ptr, *sh), _f(d.exp_avg[k], *sh), _f(d.exp_avg_sq[k], *sh)
+                    m[...] = d.beta1 * m + (1 - d.beta1) * g
+                    v[...] = d.beta2 * v + (1 - d.beta2) * g * g
+                    p[...] = p - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + d.eps)
         del self.calls[n0:]
         return 0
 

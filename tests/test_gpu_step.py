@@ -89,15 +89,17 @@ def test_graphed_step_equals_eager_steps(name, tf32):
     assert losses_g[0] != losses_g[1]                   # fresh eps every replay
 
 
-def test_fused_optimizer_matches_separate_adam_on_gpu():
-    """bbb_linear_bwd_adam (Adam in the backward epilogue) == bbb_linear_bwd + bbb_adam_step, same Philox draws.
+@pytest.mark.parametrize('network_level', [False, True])
+def test_fused_optimizer_matches_separate_adam_on_gpu(network_level):
+    """Adam in the backward's gradient write-back (bbb_mlp_bwd with an Adam descriptor / bbb_linear_bwd_adam) == the
+    same backward kernels + bbb_adam_step, same Philox draws.
     One step, so the comparison is not blurred by the TF32 path's run-to-run reorder noise feeding Adam's sign."""
     from bnn_b200 import functional as F
     c = Case('cfg2_mnist_mix')
     x, y = c.x.to(DEV), c.y.to(DEV)
     res = []
-    # (the fused optimiser rides in the per-layer backward kernel: compare it with that same kernel + bbb_adam_step)
-    monkey_prev, F.use_network_level_call = F.use_network_level_call, False
+    # (the fused optimiser rides in the backward kernel of either path: compare it with that same kernel + bbb_adam_step)
+    monkey_prev, F.use_network_level_call = F.use_network_level_call, network_level
     for fuse in (False, True, False):          # the second unfused run measures this path's run-to-run noise
         net = PC.build_net(c, DEV, tf32=True).train()
         opt = bnn_b200.FusedAdam(net.parameters(), lr=1e-3)

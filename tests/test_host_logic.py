@@ -215,9 +215,12 @@ def test_beta_may_be_a_tensor(fake):
     assert outs[0][0] == outs[1][0] and torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-9)
 
 
-def test_fused_optimizer_step_equals_backward_then_adam(fake):
-    """net.fuse_optimizer(opt): backward applies Adam inside bbb_linear_bwd_adam and leaves .grad unset; the
-    parameters after 2 steps equal backward + FusedAdam.step()."""
+@pytest.mark.parametrize('network_level', [True, False])
+def test_fused_optimizer_step_equals_backward_then_adam(fake, network_level, monkeypatch):
+    """net.fuse_optimizer(opt): backward applies Adam inside bbb_mlp_bwd (network-level call) / bbb_linear_bwd_adam
+    (per-layer calls) and leaves .grad unset; the parameters after 2 steps equal backward + FusedAdam.step()."""
+    from bnn_b200 import functional as F
+    monkeypatch.setattr(F, 'use_network_level_call', network_level)
     c = Case('small_cls_mix')
     res = []
     for fuse in (False, True):
@@ -234,7 +237,9 @@ def test_fused_optimizer_step_equals_backward_then_adam(fake):
                 assert all((p.grad is None) == fuse for p in net.parameters())
                 opt.step()
         res.append([p.detach().clone() for p in net.parameters()])
-        assert ('linear_bwd_adam' in fake.calls) == fuse
+        assert ('mlp_bwd' in fake.calls) == network_level
+        if not network_level:
+            assert ('linear_bwd_adam' in fake.calls) == fuse
     for a, b in zip(*res):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), float((a - b).abs().max())
 
