@@ -1,5 +1,7 @@
 """BayesianNetwork (networks.py:140-225) on the CUDA kernels, plus the two stock baselines the
 reference's callers import by name (MLP, MLP_Dropout: plain torch.nn, not part of the hot path)."""
+import os
+
 import torch
 from torch import nn
 
@@ -28,7 +30,9 @@ class BayesianNetwork(nn.Module):
         self.prior_init = model_params['prior_init']
         self.mixture_prior = model_params['mixture_prior']
         self.local_reparam = model_params.get('local_reparam', False)
-        self.tf32 = bool(model_params.get('tf32', False))
+        # 'tf32' key, else the process-wide default BBB_TF32=1 (the switch for callers that build model_params themselves:
+        # reg_task.py / class_task.py / bandits.py run unchanged and cannot pass the key)
+        self.tf32 = bool(model_params.get('tf32', os.environ.get('BBB_TF32', '0') == '1'))
         self.fused = bool(model_params.get('fused', True))
 
         if isinstance(self.hidden_units, (list, tuple)):
