@@ -61,6 +61,9 @@ _SIGS = {
     'bbb_logprob_reduce': ([P, P, P, U64, U32, U32, U32, P, I64, I32, P, P, P, P], C.c_int),
     'bbb_kl_gauss': ([P, P, F32, I64, P, P], C.c_int),
     'bbb_philox_fill_normal': ([P, I64, U64, U32, U32, U32, P], C.c_int),
+    'bbb_snr': ([P, P, I64, P, P], C.c_int),
+    'bbb_snr_prune': ([P, P, I64, F32, P, P], C.c_int),
+    'bbb_softmax_mean': ([P, I64, I64, I64, P, P], C.c_int),
     'bbb_nll_ce': ([P, P, I64, I64, I64, F32, P, P, P], C.c_int),
     'bbb_nll_gauss': ([P, P, F32, I64, I64, I64, F32, P, P, P], C.c_int),
     'bbb_head_fwd': ([P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I32, I32, P, F32, F32, P, P, P, P, P, F32,

@@ -98,6 +98,16 @@ __device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t *p) {
   return v;
 }
 
+// Bounded wait on a peer's flag: a rank that skips a step or dies must not leave the other GPUs spinning for ever inside a
+// kernel.  After ~2^24 polls (seconds) the waiter gives up, raises the error word (done[1], checked by the host:
+// PeerShardedAdam.check_health) and lets the kernel finish with whatever it has.
+__device__ __forceinline__ void wait_flag(const uint32_t *f, uint32_t e, uint32_t *err) {
+  for (uint32_t spin = 0; (int32_t)(ld_flag_sys(f) - e) < 0; ++spin) {
+    if (spin > (1u << 24)) { atomicExch(err, 1u); break; }
+    __nanosleep(40);
+  }
+}
+
 __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
   pdl_launch_dependents();
   pdl_wait();                         // this rank's backward (the previous kernels of the stream) is complete
@@ -112,8 +122,7 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
     st_flag_sys(a.flags[tid] + a.rank, e);
   }
   if (tid < W) {
-    const uint32_t *f = a.flags[a.rank] + tid;
-    while ((int32_t)(ld_flag_sys(f) - e) < 0) __nanosleep(20);
+    wait_flag(a.flags[a.rank] + tid, e, a.done + 1);
   }
   __syncthreads();
   const AdamConst c = cs;
@@ -163,8 +172,7 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
     if (tid < W) {
       __threadfence_system();
       st_flag_sys(a.flags[tid] + W + a.rank, e);
-      const uint32_t *f = a.flags[a.rank] + W + tid;
-      while ((int32_t)(ld_flag_sys(f) - e) < 0) __nanosleep(20);
+      wait_flag(a.flags[a.rank] + W + tid, e, a.done + 1);
     }
     __syncthreads();
     if (tid == 0) { *a.done = 0u; *a.epoch = e; }

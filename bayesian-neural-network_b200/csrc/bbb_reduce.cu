@@ -179,6 +179,53 @@ __global__ void elbo_finalize_kernel(const double *logp, const double *logq, con
   }
 }
 
+// signal-to-noise ratio in decibels of every Gaussian parameter, 10 log10(|mu| / softplus(rho)) (weight_pruning.py:81-83),
+// and/or the pruning pass of weight_pruning.py:85-115: mu, rho *= (snr > threshold), in place.  One pass over (mu, rho).
+__global__ void __launch_bounds__(RT) snr_kernel(float *__restrict__ mu, float *__restrict__ rho, int64_t n,
+                                                 float *__restrict__ snr_out, int prune, float threshold,
+                                                 unsigned long long *kept) {
+  const int64_t stride = (int64_t)gridDim.x * RT;
+  unsigned long long mine = 0;
+  for (int64_t i = (int64_t)blockIdx.x * RT + threadIdx.x; i < n; i += stride) {
+    const float m = mu[i], r = rho[i];
+    const float snr = 10.0f * log10f(fabsf(m) / softplus_f(r));
+    if (snr_out) snr_out[i] = snr;
+    if (prune) {
+      const bool keep = snr > threshold;        // (NaN and -inf, i.e. mu == 0, are dropped, as `snrs > threshold` does)
+      if (!keep) { mu[i] = m * 0.0f; rho[i] = r * 0.0f; }
+      mine += keep ? 1ull : 0ull;
+    }
+  }
+  if (prune && kept) {
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kept, mine);
+  }
+}
+
+// BNN_Classification.predict (class_task.py:81-87): softmax of every sampled forward, averaged over the samples.
+// One warp per batch row; logits [S,B,C], probs [B,C].
+__global__ void __launch_bounds__(128) softmax_mean_kernel(const float *__restrict__ logits, int64_t S, int64_t B, int64_t C,
+                                                           float *__restrict__ probs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t b = (int64_t)blockIdx.x * 4 + warp; b < B; b += (int64_t)gridDim.x * 4) {
+    for (int64_t c0 = 0; c0 < C; c0 += 32) {        // (C <= 32: one pass; wider heads accumulate chunk by chunk)
+      const int64_t c = c0 + lane;
+      float acc = 0.0f;
+      for (int64_t s = 0; s < S; ++s) {
+        const float *z = logits + (s * B + b) * C;
+        float mx = -INFINITY;
+        for (int64_t j = lane; j < C; j += 32) mx = fmaxf(mx, z[j]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.0f;
+        for (int64_t j = lane; j < C; j += 32) sum += expf(z[j] - mx);
+        sum = warp_sum(sum);
+        if (c < C) acc += expf(z[c] - mx) / sum;
+      }
+      if (c < C) probs[b * C + c] = acc / (float)S;
+    }
+  }
+}
+
 inline int grid_for(int64_t work_items, int per_cta) {
   int64_t need = (work_items + per_cta - 1) / per_cta;
   int64_t cap = (int64_t)sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
@@ -292,3 +339,29 @@ extern "C" int bbb_counter_add(uint32_t *counter, uint32_t inc, void *stream) {
 extern "C" uint64_t bbb_launch_count(void) { return bbb::g_launches.load(std::memory_order_relaxed); }
 extern "C" int bbb_version(void) { return BBB_VERSION; }
 extern "C" const char *bbb_last_error_string(void) { return last_error_buf(); }
+
+// ---- consumers of the (mu, rho) stream and of the sampled outputs ---------------------------------
+extern "C" int bbb_snr(const float *mu, const float *rho, int64_t n, float *snr_out, void *stream) {
+  BBB_CHECK_ARG(n >= 0 && ((mu && rho && snr_out) || n == 0), "null pointer or negative size");
+  if (n == 0) return BBB_OK;
+  snr_kernel<<<grid_for(n, RT * 4), RT, 0, (cudaStream_t)stream>>>(const_cast<float *>(mu), const_cast<float *>(rho), n,
+                                                                    snr_out, 0, 0.0f, nullptr);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+extern "C" int bbb_snr_prune(float *mu, float *rho, int64_t n, float threshold_db, unsigned long long *kept, void *stream) {
+  BBB_CHECK_ARG(n >= 0 && ((mu && rho) || n == 0), "null pointer or negative size");
+  if (n == 0) return BBB_OK;
+  snr_kernel<<<grid_for(n, RT * 4), RT, 0, (cudaStream_t)stream>>>(mu, rho, n, nullptr, 1, threshold_db, kept);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}
+
+extern "C" int bbb_softmax_mean(const float *logits, int64_t S, int64_t B, int64_t C, float *probs, void *stream) {
+  BBB_CHECK_ARG(S >= 1 && B >= 0 && C >= 1 && ((logits && probs) || B == 0), "null pointer or bad shape");
+  if (B == 0) return BBB_OK;
+  softmax_mean_kernel<<<grid_for(B, 4), 128, 0, (cudaStream_t)stream>>>(logits, S, B, C, probs);
+  BBB_CHECK_LAUNCH();
+  return BBB_OK;
+}

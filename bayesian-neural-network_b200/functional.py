@@ -33,6 +33,11 @@ def _rng(layer, seed, step, sample_base, step_dev):
 
 
 def _f32c(t):
+    """fp32, contiguous, detached.  The common case (an fp32 contiguous tensor seen inside autograd.Function.forward /
+    backward, where nothing is recorded) costs no torch op at all: the eager call path is host-bound, and three ops per
+    parameter tensor per pass were a third of it."""
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t if not t.requires_grad or not torch.is_grad_enabled() else t.detach()
     return t.detach().to(torch.float32).contiguous()
 
 
@@ -826,4 +831,37 @@ def philox_normal(n, device, seed=0, step=0, sample_idx=0, tensor_id=0):
     L.require_cuda(out)
     L.check(L.lib().bbb_philox_fill_normal(L.ptr(out), n, seed, step, sample_idx, tensor_id, L.stream()),
             'bbb_philox_fill_normal')
+    return out
+
+
+# =========================================================================================
+# consumers of the (mu, rho) stream and of the sampled outputs
+# =========================================================================================
+def compute_snr(mu, rho):
+    """10 log10(|mu| / softplus(rho)) in decibels (weight_pruning.py:81-83), one kernel pass."""
+    L.require_cuda(mu, rho)
+    mu, rho = _f32c(mu), _f32c(rho)
+    out = torch.empty_like(mu)
+    L.check(L.lib().bbb_snr(L.ptr(mu), L.ptr(rho), mu.numel(), L.ptr(out), L.stream()), 'bbb_snr')
+    return out
+
+
+def snr_prune_(mu, rho, threshold_db):
+    """In place: mu, rho *= (snr > threshold_db) (weight_pruning.py:101-115).  Returns the device count of kept entries."""
+    L.require_cuda(mu, rho)
+    if not (mu.dtype is torch.float32 and mu.is_contiguous() and rho.dtype is torch.float32 and rho.is_contiguous()):
+        raise RuntimeError('snr_prune_ works in place on contiguous fp32 tensors')
+    kept = torch.zeros(1, dtype=torch.int64, device=mu.device)
+    L.check(L.lib().bbb_snr_prune(L.ptr(mu), L.ptr(rho), mu.numel(), float(threshold_db), L.ptr(kept), L.stream()),
+            'bbb_snr_prune')
+    return kept
+
+
+def softmax_mean(logits):
+    """[S,B,C] sampled logits -> [B,C] mean over the samples of softmax (class_task.py:84-86), one launch."""
+    L.require_cuda(logits)
+    z = _f32c(logits)
+    S, B, Cc = z.shape
+    out = torch.empty((B, Cc), dtype=torch.float32, device=z.device)
+    L.check(L.lib().bbb_softmax_mean(L.ptr(z), S, B, Cc, L.ptr(out), L.stream()), 'bbb_softmax_mean')
     return out

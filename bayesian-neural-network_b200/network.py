@@ -95,7 +95,32 @@ class BayesianNetwork(nn.Module):
 
     def predict_proba(self, x, samples):
         """BNN_Classification.predict (class_task.py:81-87): softmax of every sampled forward, averaged."""
-        return torch.softmax(self.sample_predict(x, samples), dim=-1).mean(0)
+        return F.softmax_mean(self.sample_predict(x, samples))
+
+    # ---- SNR pruning (SURVEY 8 f3; weight_pruning.py:81-115) on the (mu, rho) stream, one kernel pass per tensor ----
+    def snr(self):
+        """SNR in decibels of every weight and bias, flattened in the order weight_pruning.get_snr... walks the layers:
+        per layer weights then biases.  Returns a 1-D device tensor."""
+        parts = []
+        for l in self.layers():
+            parts.append(F.compute_snr(l.weight_mu.data, l.weight_rho.data).reshape(-1))
+            parts.append(F.compute_snr(l.bias_mu.data, l.bias_rho.data).reshape(-1))
+        return torch.cat(parts)
+
+    def prune_weights(self, snrs, drop_percentage=0.5):
+        """prune_weights(model, snrs, drop_percentage) of weight_pruning.py:85-115: the SNR threshold is the
+        100 drop_percentage-th percentile of `snrs` (numpy semantics), then mu and rho of every weight and bias whose
+        SNR is not above it are multiplied by zero, in place.  Returns the fraction of parameters kept."""
+        import numpy as np
+        snr_threshold = float(np.percentile(snrs.detach().cpu().numpy() if torch.is_tensor(snrs) else snrs,
+                                            100 * drop_percentage))
+        kept, total = 0, 0
+        with torch.no_grad():
+            for l in self.layers():
+                for mu, rho in ((l.weight_mu, l.weight_rho), (l.bias_mu, l.bias_rho)):
+                    kept = kept + F.snr_prune_(mu.data, rho.data, snr_threshold)
+                    total += mu.numel()
+        return float(kept) / max(total, 1)
 
     def log_prior(self):
         return sum(l.log_prior for l in self.layers())

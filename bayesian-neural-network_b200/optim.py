@@ -161,7 +161,7 @@ class PeerShardedAdam(torch.optim.Optimizer):
         self.flat_m = torch.zeros(npad, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(npad, dtype=torch.float32, device=dev)
         self.flags = torch.zeros(2 * 8, dtype=torch.int32, device=dev)
-        self.words = torch.zeros(2, dtype=torch.int32, device=dev)          # call count, block counter
+        self.words = torch.zeros(4, dtype=torch.int32, device=dev)          # call count, block counter, error word
         self.offsets, off = [], 0
         with torch.no_grad():
             for p in params:
@@ -200,6 +200,12 @@ class PeerShardedAdam(torch.optim.Optimizer):
         super().load_state_dict(state_dict)
         steps = [float(st['step']) for st in self.state.values() if 'step' in st]
         self._t = int(max(steps)) if steps else 0
+
+    def check_health(self):
+        """Raise if a step's bounded wait for a peer rank expired (the kernel then finished without it).  Synchronises."""
+        if int(self.words[2]) != 0:
+            raise RuntimeError('PeerShardedAdam: a peer rank did not reach the gradient exchange within the kernel\'s '
+                               'bounded wait; parameters are no longer consistent across ranks')
 
     def release(self):
         """Stop routing this network's gradients into the shared bucket (the mapped peer memory itself stays mapped

@@ -572,6 +572,7 @@ def run_b200(args):
         return loss
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    sync_word = torch.zeros(1, dtype=torch.float32, device=dev)
 
     # eager call sequence first (also the per-step launch count), then capture the same step into a CUDA graph
     for _ in range(3):
@@ -600,6 +601,10 @@ def run_b200(args):
         evs = []
         for _ in range(n):
             flush.zero_()
+            if world > 1:
+                # device-side rendezvous OUTSIDE the bracket: every rank's timed region starts together, so host
+                # launch skew between the ranks is not booked as communication time by the exchange kernel's barrier
+                dist.all_reduce(sync_word)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if e2e:
@@ -608,8 +613,8 @@ def run_b200(args):
             else:
                 fn(x_d, y_d)
             e1.record()
-            if e2e:
-                e1.synchronize()                 # the caller reads the loss every step
+            if e2e or world > 1:
+                e1.synchronize()                 # the caller reads the loss every step (N > 1: same per-step rendezvous)
             evs.append((e0, e1))
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]

@@ -169,6 +169,16 @@ int bbb_kl_gauss(const float *mu, const float *rho, float sigma_p, int64_t n, do
 int bbb_philox_fill_normal(float *out, int64_t n, uint64_t seed, uint32_t step, uint32_t sample,
                            uint32_t tensor_id, void *stream);
 
+/* ---- consumers of the (mu, rho) stream: SNR pruning (weight_pruning.py:81-115) -------------------------------------------
+ * bbb_snr:       snr_out[i] = 10 log10(|mu_i| / softplus(rho_i))   (compute_snr, weight_pruning.py:81-83; decibels)
+ * bbb_snr_prune: mu_i, rho_i *= (snr_i > threshold_db), in place (prune_weights, weight_pruning.py:85-115: the same mask
+ *                multiplies mu AND rho, so a pruned weight keeps sigma = softplus(0)); *kept (nullable device counter) +=
+ *                number of parameters that survive.  One pass over (mu, rho), any n.
+ * bbb_softmax_mean: probs[b][c] = mean_s softmax(logits[s][b][:])[c]   (BNN_Classification.predict, class_task.py:81-87) */
+int bbb_snr(const float *mu, const float *rho, int64_t n, float *snr_out, void *stream);
+int bbb_snr_prune(float *mu, float *rho, int64_t n, float threshold_db, unsigned long long *kept, void *stream);
+int bbb_softmax_mean(const float *logits, int64_t S, int64_t B, int64_t C, float *probs, void *stream);
+
 /* ---- likelihood terms (BayesianNetwork.get_nll, networks.py:183-190) --------------------
  * nll += sum over (s, b) of the negative log likelihood; dout (nullable) = grad_scale * d nll / d out.
  * bbb_nll_ce:    logits [S,B,C], target int64 [B]       (CrossEntropyLoss(reduction='sum'))
@@ -272,7 +282,9 @@ int bbb_adam_step(int32_t n_tensors, float *const *params, const float *const *g
  * gradient is the MEAN over the ranks (each rank holds the gradient of its own Monte-Carlo samples).
  *   grads / params / flags   pointers to every rank's buffers AS MAPPED IN THIS PROCESS (cudaIpcOpenMemHandle, or the
  *                            same process for several devices); flags: 2*world zero-initialised uint32 per rank
- *   epoch, done_blocks       two zero-initialised device words of THIS rank (call count, block counter)
+ *   epoch, done_blocks       zero-initialised device words of THIS rank: epoch[0] = call count; done_blocks[0] = block
+ *                            counter, done_blocks[1] = error word, set to 1 when a peer did not show up within the
+ *                            kernel's bounded wait (seconds): the results of that call are then undefined
  * Every rank must make the call once per step, on any stream; the kernel completes only when all ranks have
  * finished with this rank's buffers.  world == 1 degenerates to a flat single-tensor Adam. */
 #define BBB_MAX_PEERS 8

@@ -396,6 +396,29 @@ class FakeLib:
         p[...] = p - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + eps)
         return 0
 
+    def bbb_snr(self, mu, rho, n, out, st):
+        M, Rr = _f(mu, n).astype(np.float64), _f(rho, n).astype(np.float64)
+        with np.errstate(divide='ignore'):
+            _f(out, n)[...] = (10 * np.log10(np.abs(M) / CF.softplus(Rr))).astype(np.float32)
+        return 0
+
+    def bbb_snr_prune(self, mu, rho, n, thr, kept, st):
+        M, Rr = _f(mu, n), _f(rho, n)
+        with np.errstate(divide='ignore'):
+            snr = (10 * np.log10(np.abs(M.astype(np.float64)) / CF.softplus(Rr.astype(np.float64)))).astype(np.float32)
+        keep = snr > np.float32(thr)
+        M[...] = M * keep
+        Rr[...] = Rr * keep
+        if kept:
+            _arr(kept, C.c_int64, 1)[0] += int(keep.sum())
+        return 0
+
+    def bbb_softmax_mean(self, logits, S, B, Cc, probs, st):
+        Z = _f(logits, S, B, Cc).astype(np.float64)
+        E = np.exp(Z - Z.max(-1, keepdims=True))
+        _f(probs, B, Cc)[...] = (E / E.sum(-1, keepdims=True)).mean(0).astype(np.float32)
+        return 0
+
     def bbb_timing_enable(self, on):
         return 0
 

@@ -157,3 +157,28 @@ def check_batched_prediction(case, device, samples=4, rtol=1e-5):
             p = net.predict_proba(x, samples)
         np.testing.assert_allclose(p.sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
         np.testing.assert_allclose(p.cpu().numpy(), torch.softmax(want, -1).mean(0).numpy(), rtol=1e-4, atol=1e-6)
+
+
+def check_snr_pruning(case, device, drop=0.4):
+    """net.snr() / net.prune_weights() (bbb_snr, bbb_snr_prune) against the oracle's restatement of
+    weight_pruning.py:81-115.  Elements whose SNR sits within fp32 round-off of the threshold may fall either way."""
+    from oracle import bbb_oracle as O
+    net = build_net(case, device)
+    want = O.network_snrs(case.layers)
+    got = net.snr().cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-5)
+    frac = net.prune_weights(want, drop)
+    pruned = O.prune_layers(case.layers, want, drop)
+    thr = float(np.percentile(want.numpy(), 100 * drop))
+    n_total, n_kept = 0, 0
+    for li, layer in enumerate(net.layers()):
+        snr_w = O.compute_snr(case.layers[li][0], case.layers[li][1])
+        snr_b = O.compute_snr(case.layers[li][2], case.layers[li][3])
+        for pi, pn in enumerate(PNAMES):
+            g, w = getattr(layer, pn).detach().cpu().numpy(), pruned[li][pi].numpy()
+            edge = np.abs((snr_w if pi < 2 else snr_b).numpy() - thr) < 1e-4
+            assert np.array_equal(g[~edge], w[~edge]), (li, pn)
+            n_total += g.size
+        n_kept += int((pruned[li][0] != 0).sum()) + int((pruned[li][2] != 0).sum())
+    assert abs(frac - n_kept / (n_total / 2)) < 0.02
+    assert abs(frac - (1 - drop)) < 0.05

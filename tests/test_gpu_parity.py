@@ -41,6 +41,11 @@ def test_batched_prediction(name):
     PC.check_batched_prediction(Case(name), DEV)
 
 
+@pytest.mark.parametrize('name', ['small_cls_mix', 'deep5_small_mix', 'cfg2_mnist_mix'])
+def test_snr_pruning_matches_oracle(name):
+    PC.check_snr_pruning(Case(name), DEV)
+
+
 def test_native_library_is_loaded():
     import ctypes
     assert isinstance(bnn_b200._lib.lib(), ctypes.CDLL)

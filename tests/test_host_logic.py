@@ -257,6 +257,11 @@ def test_batched_prediction(fake, name):
     PC.check_batched_prediction(Case(name), 'cpu')
 
 
+@pytest.mark.parametrize('name', ['small_cls_mix', 'deep5_small_mix'])
+def test_snr_pruning(fake, name):
+    PC.check_snr_pruning(Case(name), 'cpu')
+
+
 def test_peer_comm_struct_matches_header():
     """ctypes mirror of struct bbb_peer_comm: array lengths follow BBB_MAX_PEERS, field order follows include/bbb.h."""
     import ctypes as C

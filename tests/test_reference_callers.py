@@ -116,6 +116,40 @@ def _drive_mc_dropout(dev):
     assert out.shape == (8, 5) and torch.isfinite(out).all() and out.abs().max() > 0
 
 
+def _state_dict_round_trip(dev, local_reparam):
+    """a model trained by the drop-in loads into the REFERENCE's BayesianNetwork (load_model_utils.py:9-28
+    does model.load_state_dict(torch.load(path))) and back: same keys, same [out,in] / [in,out] layouts, and the
+    reference's mean-weight forward on the loaded parameters equals the drop-in's."""
+    import importlib.util
+    import networks as dropin                              # the drop-in (ROOT is first on sys.path)
+    d = _ref_dir()
+    spec = importlib.util.spec_from_file_location('ref_networks_original', os.path.join(d, 'networks.py'))
+    refnet = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refnet)                        # `from config import *` resolves to the drop-in config: DEVICE only
+    mp = dict(input_shape=16, classes=5, batch_size=8, hidden_units=12, mode='classification', mu_init=[-0.2, 0.2],
+              rho_init=[-5, -4], prior_init=[1.] if local_reparam else [0.5, -0, -6], mixture_prior=not local_reparam,
+              local_reparam=local_reparam)
+    torch.manual_seed(3)
+    mine = dropin.BayesianNetwork(mp).to(dev)
+    path = os.path.join(os.getcwd(), 'model.pt')
+    torch.save(mine.state_dict(), path)
+    ref = refnet.BayesianNetwork(mp)
+    ref.load_state_dict(torch.load(path, map_location='cpu'))          # strict: keys and shapes must match exactly
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    x = torch.rand(8, 1, 4, 4)
+    if not local_reparam:                                  # (the reference's LR eval branch raises AttributeError: App. B-4)
+        ref.eval(); mine.eval()
+        with torch.no_grad():
+            np.testing.assert_allclose(mine(x.to(dev)).cpu().numpy(), ref(x).numpy(), rtol=1e-5, atol=1e-6)
+    # and back: a reference checkpoint into the drop-in
+    torch.manual_seed(4)
+    ref2 = refnet.BayesianNetwork(mp)
+    torch.save(ref2.state_dict(), path)
+    mine.load_state_dict(torch.load(path, map_location=dev))
+    for (k, a), (_, b) in zip(mine.state_dict().items(), ref2.state_dict().items()):
+        assert torch.equal(a.cpu(), b), k
+
+
 def _cpu_double(monkeypatch):
     """No GPU here: the C ABI is the test double, which needs eps injected (the reference's own CPU draws)."""
     import bnn_b200
@@ -139,6 +173,18 @@ def test_reference_classification_task_on_dropin_cpu_double(ref, monkeypatch, lo
 def test_reference_bandit_on_dropin_cpu_double(ref, monkeypatch):
     _cpu_double(monkeypatch)
     _drive_bandit('cpu')
+
+
+@pytest.mark.parametrize('local_reparam', [False, True])
+def test_state_dict_round_trip_with_the_reference_cpu_double(ref, monkeypatch, local_reparam):
+    _cpu_double(monkeypatch)
+    _state_dict_round_trip('cpu', local_reparam)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('local_reparam', [False, True])
+def test_state_dict_round_trip_with_the_reference_gpu(ref, local_reparam):
+    _state_dict_round_trip('cuda', local_reparam)
 
 
 def test_reference_mc_dropout_baselines_on_dropin(ref, monkeypatch):
