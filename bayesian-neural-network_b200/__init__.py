@@ -8,7 +8,9 @@ from .layers import ScaleMixtureGaussian, GaussianNode, BayesianLinear, Bayesian
 from .network import BayesianNetwork, MLP, MLP_Dropout
 from .optim import FusedAdam, PeerShardedAdam
 from .graphed import GraphedTrainStep
+from .bandit import ReplayRing, GraphedBanditUpdate, reference_idx_pool, make_bandit_update
 
 __all__ = ['ScaleMixtureGaussian', 'GaussianNode', 'BayesianLinear', 'BayesianLinearLR', 'BayesianNetwork',
            'MLP', 'MLP_Dropout', 'set_eps_mode', 'get_eps_mode', 'manual_seed', 'eps_mode', 'set_sample_base',
-           'use_device_step', 'functional', 'rng', 'parallel', 'FusedAdam', 'PeerShardedAdam', 'GraphedTrainStep']
+           'use_device_step', 'functional', 'rng', 'parallel', 'FusedAdam', 'PeerShardedAdam', 'GraphedTrainStep',
+           'ReplayRing', 'GraphedBanditUpdate', 'reference_idx_pool', 'make_bandit_update']
