@@ -133,7 +133,15 @@ class BayesianNetwork(nn.Module):
 
     def get_nll(self, outputs, target, sigma=1.):
         if self.mode == 'regression':
-            nll = -torch.distributions.Normal(outputs, sigma).log_prob(target).sum()
+            # -Normal(outputs, sigma).log_prob(target).sum() (networks.py:185) written out -- same arithmetic and the same
+            # broadcasting of target against outputs -- because the distribution object turns a python
+            # sigma into a device tensor with a host-to-device copy, which a CUDA-graph capture does not allow
+            if torch.is_tensor(sigma):
+                nll = -torch.distributions.Normal(outputs, sigma).log_prob(target).sum()
+            else:
+                import math
+                var = float(sigma) ** 2
+                nll = -(-((target - outputs) ** 2) / (2 * var) - math.log(float(sigma)) - math.log(math.sqrt(2 * math.pi))).sum()
         elif self.mode == 'classification':
             nll = nn.CrossEntropyLoss(reduction='sum')(outputs, target)
         else:
