@@ -138,8 +138,8 @@ class GraphedBanditUpdate:
                 p.copy_(snap)
             for st in opt.state.values():
                 for t in st.values():
-                    if torch.is_tensor(t) and id(t) in s_snap:
-                        t.copy_(s_snap[id(t)])
+                    if torch.is_tensor(t):      # (state created by the warm-up itself starts from zero, as a fresh one does)
+                        t.copy_(s_snap[id(t)]) if id(t) in s_snap else t.zero_()
         self.counter.fill_(c_base)
         torch.cuda.synchronize()
         self.graphs[n] = (g, info)
