@@ -719,10 +719,10 @@ def run_b200(args):
                     peak_source='MEASURED_PEAKS.json hbm_gbs (measured)' if peaks else 'fallback 6650 GB/s',
                     algorithmic_bytes_per_launch=agg[top]['bytes'])
         try:      # DRAM bytes of the same kernel from the committed ncu --set full capture (per launch), if present
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))
             if args.workload == 'mnist' and top in tr['kernels']:
                 roof['traffic'] = tr['kernels'][top]['dram_bytes']
-                roof['traffic_source'] = 'profiles/r1_traffic.json (' + tr['kernels'][top]['kernel'] + ')'
+                roof['traffic_source'] = 'profiles/r2_traffic.json (' + tr['kernels'][top]['kernel'] + ')'
         except Exception:
             pass
         if args.workload == 'wide':
