@@ -11,10 +11,13 @@ import bnn_b200  # noqa: E402
 from bnn_b200 import functional as F, parallel  # noqa: E402
 
 
+TF32 = '--tf32' in sys.argv
+
+
 def build(dev):
     torch.manual_seed(0)
     mp = dict(input_shape=784, classes=10, batch_size=128, hidden_units=1200, mode='classification',
-              mu_init=[-0.2, 0.2], rho_init=[-5, -4], prior_init=[0.5, 0, -8], mixture_prior=True, tf32=False)
+              mu_init=[-0.2, 0.2], rho_init=[-5, -4], prior_init=[0.5, 0, -8], mixture_prior=True, tf32=TF32)
     return bnn_b200.BayesianNetwork(mp).to(dev).train()
 
 
@@ -41,6 +44,8 @@ def main():
                 parallel.allreduce_gradients(net, world)
             opt.step()
         torch.cuda.synchronize()
+        if peer:
+            opt.check_health()
         res.append([p.detach().clone() for p in net.parameters()])
     worst = 0.0
     for a, b in zip(*res):
@@ -51,8 +56,9 @@ def main():
     ref = flat.clone()
     dist.broadcast(ref, 0)
     same = bool(torch.equal(flat, ref))
-    print(f'rank {rank}: mismatching fraction vs all-reduce + FusedAdam {worst:.2e}; identical across ranks: {same}', flush=True)
-    assert worst < 1e-3 and same
+    print(f'rank {rank} of {world} ({"tf32 network-level kernels" if TF32 else "exact fp32 kernels"}): mismatching fraction vs all-reduce + FusedAdam {worst:.2e}; identical across ranks: {same}', flush=True)
+    # (TF32 mode: the split-K reduce-add order varies from run to run, so a few round-off-sized gradients flip Adam's sign)
+    assert worst < (2e-2 if TF32 else 1e-3) and same
     dist.barrier()
     os._exit(0)
 
