@@ -28,6 +28,31 @@ struct AdamArgs {
   const float *lr_scale_dev;
 };
 
+// One 16-byte quad of one tensor: where it lives and whether it can be moved with vector accesses.
+struct QuadRef {
+  float *p, *m, *v;
+  const float *g;
+  int valid;     // elements of the quad inside the tensor (4 unless it is the tensor's tail)
+  bool vec;
+};
+__device__ __forceinline__ QuadRef locate(const AdamArgs &a, int64_t q, int &ti) {
+  while (q >= a.qend[ti]) ++ti;
+  const int64_t e = (q - (ti ? a.qend[ti - 1] : 0)) * 4;
+  QuadRef r;
+  r.p = a.p[ti] + e; r.m = a.m[ti] + e; r.v = a.v[ti] + e; r.g = a.g[ti] + e;
+  r.valid = (int)min((int64_t)4, a.size[ti] - e);
+  r.vec = r.valid == 4 && a.vec[ti];
+  return r;
+}
+// the SFU's sqrt and reciprocal are accurate to 1 ulp-level (2^-23 relative); the update term they feed is lr times
+// smaller than the parameter, so the result equals torch's to far below fp32 round-off of p (tests: rtol 2e-6)
+__device__ __forceinline__ void adam4(float4 &P, const float4 &G, float4 &M, float4 &V, const AdamConst &c, float ibc) {
+  adam1_fast(P.x, G.x, M.x, V.x, c, ibc);
+  adam1_fast(P.y, G.y, M.y, V.y, c, ibc);
+  adam1_fast(P.z, G.z, M.z, V.z, c, ibc);
+  adam1_fast(P.w, G.w, M.w, V.w, c, ibc);
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   pdl_launch_dependents();
   pdl_wait();
@@ -35,29 +60,38 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   if (threadIdx.x == 0) cs = adam_consts(a.lr, a.b1, a.b2, a.eps, a.step, a.step_dev, a.lr_scale_dev);
   __syncthreads();
   const AdamConst c = cs;
+  const float ibc = 1.0f / c.bc2_sqrt;
   const int64_t total = a.qend[a.n - 1], stride = (int64_t)gridDim.x * blockDim.x;
-  int ti = 0;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
-    while (q >= a.qend[ti]) ++ti;
-    const int64_t e = (q - (ti ? a.qend[ti - 1] : 0)) * 4;
-    const int valid = (int)min((int64_t)4, a.size[ti] - e);
-    float *pp = a.p[ti] + e, *pm = a.m[ti] + e, *pv = a.v[ti] + e;
-    const float *pg = a.g[ti] + e;
-    if (valid == 4 && a.vec[ti]) {
-      float4 P = *reinterpret_cast<float4 *>(pp), M = *reinterpret_cast<float4 *>(pm), V = *reinterpret_cast<float4 *>(pv);
-      const float4 G = *reinterpret_cast<const float4 *>(pg);
-      adam1(P.x, G.x, M.x, V.x, c);
-      adam1(P.y, G.y, M.y, V.y, c);
-      adam1(P.z, G.z, M.z, V.z, c);
-      adam1(P.w, G.w, M.w, V.w, c);
-      *reinterpret_cast<float4 *>(pp) = P;
-      *reinterpret_cast<float4 *>(pm) = M;
-      *reinterpret_cast<float4 *>(pv) = V;
+  int t0 = 0, t1 = 0;
+  // two quads per thread and iteration: all eight 16-byte loads are in flight before the first update is formed
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += 2 * stride) {
+    const QuadRef r0 = locate(a, q, t0);
+    const bool two = q + stride < total;
+    QuadRef r1 = r0;
+    if (two) r1 = locate(a, q + stride, t1);
+    if (r0.vec && r1.vec) {
+      float4 P0 = *reinterpret_cast<float4 *>(r0.p), M0 = *reinterpret_cast<float4 *>(r0.m), V0 = *reinterpret_cast<float4 *>(r0.v);
+      const float4 G0 = *reinterpret_cast<const float4 *>(r0.g);
+      float4 P1 = *reinterpret_cast<float4 *>(r1.p), M1 = *reinterpret_cast<float4 *>(r1.m), V1 = *reinterpret_cast<float4 *>(r1.v);
+      const float4 G1 = *reinterpret_cast<const float4 *>(r1.g);
+      adam4(P0, G0, M0, V0, c, ibc);
+      *reinterpret_cast<float4 *>(r0.p) = P0;
+      *reinterpret_cast<float4 *>(r0.m) = M0;
+      *reinterpret_cast<float4 *>(r0.v) = V0;
+      if (two) {
+        adam4(P1, G1, M1, V1, c, ibc);
+        *reinterpret_cast<float4 *>(r1.p) = P1;
+        *reinterpret_cast<float4 *>(r1.m) = M1;
+        *reinterpret_cast<float4 *>(r1.v) = V1;
+      }
     } else {
-      for (int j = 0; j < valid; ++j) {
-        float P = pp[j], M = pm[j], V = pv[j];
-        adam1(P, pg[j], M, V, c);
-        pp[j] = P; pm[j] = M; pv[j] = V;
+      for (int k = 0; k < (two ? 2 : 1); ++k) {
+        const QuadRef &r = k ? r1 : r0;
+        for (int j = 0; j < r.valid; ++j) {
+          float P = r.p[j], M = r.m[j], V = r.v[j];
+          adam1_fast(P, r.g[j], M, V, c, ibc);
+          r.p[j] = P; r.m[j] = M; r.v[j] = V;
+        }
       }
     }
   }
@@ -270,7 +304,7 @@ extern "C" int bbb_adam_step(int32_t n_tensors, float *const *params, const floa
   a.n = n; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = (float)eps; a.step = step; a.step_dev = step_dev;
   a.lr_scale_dev = lr_scale_dev;
   int64_t blocks = (q + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)sm_count() * 4;   // one resident wave (4 CTAs of 256 threads x 56 registers per SM)
   if (blocks > cap) blocks = cap;
   BBB_CHECK_CUDA(launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a));
   BBB_CHECK_LAUNCH();

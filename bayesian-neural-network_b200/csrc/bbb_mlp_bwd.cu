@@ -178,10 +178,9 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc1 = idesc_tf32_major(128, N, 1, 1);   // G  = dz^T x : A, B MN-major
       constexpr uint32_t idesc2 = idesc_tf32_major(128, N, 0, 1);   // dX = dz W  : A K-major, B MN-major
-      int rit = 0, dzk_it = 0;
+      int rit = 0, dzk_it = 0, wph = 0;
       for (int g = 0; g < groups; ++g) {
         const int s0 = 2 * g, ns = min(2, a.S - s0);
-        const uint32_t gph = (uint32_t)(g & 1);
         for (int s = 0; s < ns; ++s) {
           for (int ch = 0; ch < 4; ++ch, ++rit) {
             const int slot = rit % NRING;
@@ -198,15 +197,29 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         }
         mma_commit(smem_u32(&ctl.g_full));
         if (kDx) {
-          mbar_wait_parked(smem_u32(&ctl.w_full), gph);            // both weight tiles are complete
+          // dgrad.  Sample 0 region by region (N = 32) as the epilogue completes each 32-column region of the weight
+          // tiles -- only the last region's MMAs are left when the epilogue ends --; sample 1 in one piece once its
+          // K-major dz tile has replaced sample 0's.
+          constexpr uint32_t idesc2r = idesc_tf32_major(128, 32, 0, 1);
           const int nk = (rows + 7) >> 3;
-          for (int s = 0; s < ns; ++s, ++dzk_it) {
-            mbar_wait_parked(smem_u32(&ctl.dzk_full), (uint32_t)(dzk_it & 1));
+          mbar_wait_parked(smem_u32(&ctl.dzk_full), (uint32_t)(dzk_it & 1));
+          ++dzk_it;
+          for (int r = 0; r < XWR; ++r, ++wph) {
+            mbar_wait_parked(smem_u32(&ctl.w_full), (uint32_t)(wph & 1));
             tc_fence_after_sync();
             for (int k8 = 0; k8 < nk; ++k8)
-              mma_tf32(tm_dx[s], smem_desc_sw128(dzk + (k8 >> 2) * REG + (k8 & 3) * 32),
-                       smem_desc_mn32(w_s[s] + k8 * 1024, REG), idesc2, k8 ? 1u : 0u);
-            mma_commit(smem_u32(&ctl.dx_full[s]));
+              mma_tf32(tm_dx[0] + 32 * r, smem_desc_sw128(dzk + (k8 >> 2) * REG + (k8 & 3) * 32),
+                       smem_desc_mn32(w_s[0] + r * REG + k8 * 1024, REG), idesc2r, k8 ? 1u : 0u);
+          }
+          mma_commit(smem_u32(&ctl.dx_full[0]));
+          if (ns > 1) {
+            mbar_wait_parked(smem_u32(&ctl.dzk_full), (uint32_t)(dzk_it & 1));
+            ++dzk_it;
+            tc_fence_after_sync();
+            for (int k8 = 0; k8 < nk; ++k8)
+              mma_tf32(tm_dx[1], smem_desc_sw128(dzk + (k8 >> 2) * REG + (k8 & 3) * 32),
+                       smem_desc_mn32(w_s[1] + k8 * 1024, REG), idesc2, k8 ? 1u : 0u);
+            mma_commit(smem_u32(&ctl.dx_full[1]));
           }
         }
       }
@@ -348,6 +361,11 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
           sts128(stg + stg_off(row, c16), osc * gm[0], osc * gm[1], osc * gm[2], osc * gm[3]);
           sts128(stg + REG + stg_off(row, c16), osc * gr[0], osc * gr[1], osc * gr[2], osc * gr[3]);
         }
+        if (kDx) {      // this warp's part of the region's weight tiles is complete: dgrad of the region may start
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_l(smem_u32(&ctl.w_full));
+        }
         // coalesced write-back of the region: a quarter warp per row.  With the fused optimiser the parameter and its
         // Adam state are requested BEFORE the barrier (the sampling registers are dead by now), so their latency hides
         // behind it; the update replaces the gradient store.
@@ -412,11 +430,7 @@ ws_bwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         if (g == 0 && r < 3) stamp(tl, 5 + r);
       }
       if (kDx) {
-        // ---- dgrad: the weight tiles are complete -> MMA2; then dX_s [lane = b][column = i] -> mask -> red.add ------------
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_l(smem_u32(&ctl.w_full));
+        // ---- dgrad: dX_s [lane = b][column = i] -> mask -> red.add ----------------------------------------------------------
         if (g == 0) stamp(tl, 8);
         for (int s = 0; s < ns; ++s) {
           // the activations this layer consumed (the (x > 0) mask), in the coalesced mapping: requested before the wait
