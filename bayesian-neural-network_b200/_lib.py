@@ -41,7 +41,7 @@ class MlpLayer(C.Structure):
     """struct bbb_mlp_layer: one layer of a network-level call (bbb_mlp_fwd / bbb_mlp_bwd)"""
     _fields_ = [('w_mu', C.c_void_p), ('w_rho', C.c_void_p), ('b_mu', C.c_void_p), ('b_rho', C.c_void_p),
                 ('eps_w', C.c_void_p), ('eps_b', C.c_void_p), ('inn', C.c_int64), ('out', C.c_int64),
-                ('y', C.c_void_p), ('dz', C.c_void_p),
+                ('y', C.c_void_p), ('w_sample', C.c_void_p), ('dz', C.c_void_p),
                 ('g_w_mu', C.c_void_p), ('g_w_rho', C.c_void_p), ('g_b_mu', C.c_void_p), ('g_b_rho', C.c_void_p)]
 
 

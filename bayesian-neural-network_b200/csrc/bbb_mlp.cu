@@ -135,7 +135,7 @@ MlpLayerDesc make_desc(const bbb_mlp_layer &L, const float *x, bool x_shared) {
   d.x = x; d.x_shared = x_shared;
   d.w_mu = L.w_mu; d.w_rho = L.w_rho; d.b_mu = L.b_mu; d.b_rho = L.b_rho; d.eps_w = L.eps_w; d.eps_b = L.eps_b;
   d.in = L.in; d.out = L.out;
-  d.y = L.y;
+  d.y = L.y; d.w_sample = L.w_sample;
   d.dz = L.dz; d.g_w_mu = L.g_w_mu; d.g_w_rho = L.g_w_rho; d.g_b_mu = L.g_b_mu; d.g_b_rho = L.g_b_rho;
   return d;
 }
@@ -192,6 +192,15 @@ extern "C" int bbb_mlp_fwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
   r.layer = (uint32_t)(n_layers - 1);
   const int32_t head_flags = (flags & (BBB_F_SAMPLE | BBB_F_LOGPROB)) | BBB_F_RELU_IN;    // its input is a pre-activation
   ScopedTimer tm("head_fwd[%lldx%lld]", (long long)H.in, (long long)H.out, st);
+  if (H.w_sample && head2_supported(S, B, H.in, H.out) && (!out4 || done_counter)) {
+    BBB_CHECK_ARG(nll_kind == BBB_NLL_NONE || nll_kind == BBB_NLL_CE || nll_kind == BBB_NLL_GAUSS, "bad nll_kind");
+    BBB_CHECK_ARG(nll_kind == BBB_NLL_NONE || (target && nll), "target and nll accumulator required");
+    BBB_CHECK_ARG(nll_kind != BBB_NLL_GAUSS || sigma > 0, "sigma must be positive");
+    BBB_CHECK_ARG(done_counter, "the full-grid head needs done_counter (two zeroed words)");
+    MlpLayerDesc d = make_desc(H, inp, false);
+    return launch_head2_fwd(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, head_flags, nll_kind, target, sigma, grad_scale,
+                            d_out, logp, logq, nll, beta, beta_dev, out4, done_counter, st);
+  }
   return bbb_head_fwd(inp, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b, rng ? &r : nullptr, prior, S, B,
                       H.in, H.out, head_flags, nll_kind, target, sigma, grad_scale, H.y, d_out, logp, logq, nll, beta,
                       beta_dev, out4, done_counter, stream);
@@ -235,7 +244,13 @@ extern "C" int bbb_mlp_bwd(const bbb_mlp_layer *layers, int32_t n_layers, const 
     bbb_rng r = rng ? *rng : bbb_rng{};
     r.layer = (uint32_t)(n_layers - 1);
     ScopedTimer tm("head_bwd[%lldx%lld]", (long long)H.in, (long long)H.out, st);
-    if (int rc = bbb_linear_bwd(H.dz, nullptr, P.y, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b,
+    if (H.w_sample && head2_supported(S, B, H.in, H.out)) {
+      MlpLayerDesc d = make_desc(H, P.y, false);
+      d.dx = P.dz;
+      if (int rc = launch_head2_bwd(d, S, B, make_rng_dev(rng ? &r : nullptr), pd, keep | BBB_F_RELU_IN, gp, gq, gp_dev, gq_dev,
+                                    (int)g_dev_stride, out_scale_dev, st))
+        return rc;
+    } else if (int rc = bbb_linear_bwd(H.dz, nullptr, P.y, B * H.in, H.w_mu, H.w_rho, H.b_mu, H.b_rho, H.eps_w, H.eps_b,
                                 rng ? &r : nullptr, prior, S, B, H.in, H.out,
                                 keep | BBB_F_RELU_IN | BBB_F_DX_PREACT | BBB_F_OUT_ZEROED, gp, gq, gp_dev, gq_dev,
                                 g_dev_stride, out_scale_dev, P.dz, H.g_w_mu, H.g_w_rho, H.g_b_mu, H.g_b_rho, stream))

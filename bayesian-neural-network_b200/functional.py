@@ -423,7 +423,7 @@ def _layerwise_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, n
     return ys, dxs, d_out
 
 
-def _mlp_layer_table(params, eps, ys, dzs, grads):
+def _mlp_layer_table(params, eps, ys, dzs, grads, head_scratch=None):
     tab = (L.MlpLayer * len(params))()
     for l, p in enumerate(params):
         t = tab[l]
@@ -433,6 +433,7 @@ def _mlp_layer_table(params, eps, ys, dzs, grads):
         t.y, t.dz = L.ptr(ys[l]), L.ptr(dzs[l])
         if grads is not None and grads[l] is not None:
             t.g_w_mu, t.g_w_rho, t.g_b_mu, t.g_b_rho = (g.data_ptr() for g in grads[l])
+    tab[len(params) - 1].w_sample = L.ptr(head_scratch)
     return tab
 
 
@@ -457,7 +458,9 @@ def _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_gr
     dzs = (ws[1 + len(hidden):] if need_grad else [None] * len(hidden))
     logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
     d_out = torch.empty((S, B, Cc), dtype=torch.float32, device=dev) if need_grad else None
-    tab = _mlp_layer_table(params, eps, ys, list(dzs) + [d_out], None)
+    # the head's sampled weights (+ biases): written once by its forward, reused by its backward
+    hs = torch.empty(S * Cc * params[-1][0].shape[1] + 16 * S, dtype=torch.float32, device=dev)
+    tab = _mlp_layer_table(params, eps, ys, list(dzs) + [d_out], None, hs)
     kind = L.NLL_CE if mode == 'classification' else L.NLL_GAUSS
     tgt = target if mode == 'classification' else _f32c(target)
     rng = eps.rng(0)
@@ -465,7 +468,7 @@ def _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_gr
                                 L.F_SAMPLE | L.F_LOGPROB | L.F_TF32, kind, L.ptr(tgt), float(sigma), 1.0 / S,
                                 L.ptr(d_out), L.ptr(logp), L.ptr(logq), L.ptr(nll), beta_h, L.ptr(beta_d), L.ptr(out4),
                                 L.ptr(done), L.stream()), 'bbb_mlp_fwd')
-    return ys, ([None] + list(dzs) if need_grad else None), d_out
+    return ys, ([None] + list(dzs) + [hs] if need_grad else None), d_out
 
 
 class _FusedELBO(torch.autograd.Function):
@@ -528,7 +531,8 @@ class _FusedELBO(torch.autograd.Function):
             with torch.no_grad():
                 B = x2.shape[0]
                 hg = _alloc_grads(params[-1:])
-                tab = _mlp_layer_table(params, eps, ys, list(ctx.dxs[1:]) + [d_out], [None] * (nl - 1) + [hg[0]])
+                tab = _mlp_layer_table(params, eps, ys, list(ctx.dxs[1:nl]) + [d_out], [None] * (nl - 1) + [hg[0]],
+                                       ctx.dxs[nl])
                 adam = (L.AdamFuse * nl)()
                 for l in range(nl):
                     d = ctx.fused_opt.fuse_descriptor(ctx.live[l])
@@ -548,8 +552,8 @@ class _FusedELBO(torch.autograd.Function):
             # zero-filled gradient w.r.t. hidden layer l's pre-activation output
             grads = _alloc_grads(params)
             B = x2.shape[0]
-            dzs = list(ctx.dxs[1:]) + [d_out]
-            tab = _mlp_layer_table(params, eps, ys, dzs, grads)
+            dzs = list(ctx.dxs[1:nl]) + [d_out]
+            tab = _mlp_layer_table(params, eps, ys, dzs, grads, ctx.dxs[nl])
             rng = eps.rng(0)
             L.check(L.lib().bbb_mlp_bwd(tab, nl, L.ptr(x2), S, B, C.byref(rng), C.byref(prior), L.F_SAMPLE | L.F_TF32,
                                         -beta / S, beta / S, L.ptr(bd), L.ptr(bd), 0, L.ptr(scale), None, L.stream()),

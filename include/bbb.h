@@ -230,6 +230,10 @@ typedef struct bbb_mlp_layer {
   const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_w, *eps_b;
   int64_t in, out;
   float *y;                                       /* [S,B,out] pre-activation output (hidden layers: zero-filled)          */
+  float *w_sample;                                /* last layer only, nullable: scratch of S*out*in + 16*S floats.  When given,
+                                                     the head runs on the full-grid kernels of csrc/bbb_head2.cu (weights sampled
+                                                     once into the scratch, which the backward reuses) and done_counter must
+                                                     point to TWO zeroed words; NULL: the cluster head of bbb_head_fwd        */
   float *dz;                                      /* [S,B,out]: hidden layers zero-filled, accumulated by the layer above */
   float *g_w_mu, *g_w_rho, *g_b_mu, *g_b_rho;     /* parameter gradients, overwritten                                     */
 } bbb_mlp_layer;
