@@ -378,6 +378,9 @@ def mlp_forward(x2, layers, prior, S, sample=True, logprob=True, tf32=False):
 # sample_elbo in TF32 mode goes through ONE C call per network pass (bbb_mlp_fwd / bbb_mlp_bwd) when the library covers
 # the network (bbb_mlp_supported); False forces the per-layer calls (A/B measurements, tools/check_mlp.py)
 use_network_level_call = True
+# the head on a full grid (csrc/bbb_head2.cu) instead of the 8-CTA-cluster head: measured SLOWER on B200 (23.6 + 21.0 us
+# against 16.0 + 9.4 us by ncu, cfg2), so it stays opt-in -- DESIGN.md 4.7
+use_full_grid_head = False
 
 
 def _layerwise_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_grad, tf32, beta_h, beta_d, out4):
@@ -459,7 +462,8 @@ def _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_gr
     logp, logq, nll = acc[:S], acc[S:2 * S], acc[2 * S:]
     d_out = torch.empty((S, B, Cc), dtype=torch.float32, device=dev) if need_grad else None
     # the head's sampled weights (+ biases): written once by its forward, reused by its backward
-    hs = torch.empty(S * Cc * params[-1][0].shape[1] + 16 * S, dtype=torch.float32, device=dev)
+    hs = (torch.empty(S * Cc * params[-1][0].shape[1] + 16 * S, dtype=torch.float32, device=dev)
+          if use_full_grid_head else None)
     tab = _mlp_layer_table(params, eps, ys, list(dzs) + [d_out], None, hs)
     kind = L.NLL_CE if mode == 'classification' else L.NLL_GAUSS
     tgt = target if mode == 'classification' else _f32c(target)
