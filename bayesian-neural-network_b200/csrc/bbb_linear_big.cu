@@ -19,6 +19,8 @@
 //   Grid (weight-row tiles, batch tiles of 512, samples); batch tile 0 also accumulates the log-prob terms.
 // W never leaves the SM; eps is regenerated from the same Philox coordinates in the backward.
 #include "bbb_tc_tiles.cuh"
+#include "bbb_tma.cuh"
+#include <cstring>
 
 namespace bbb {
 namespace {
@@ -257,7 +259,7 @@ constexpr int WSTAGE = WA_BYTES + WB_BYTES;
 constexpr int kWgradDyn = WSTG * WSTAGE + 1024;
 
 struct WCtl {
-  uint64_t full[WSTG], empty[WSTG], acc;
+  uint64_t full[WSTG], fixed[WSTG], empty[WSTG], acc;
   uint32_t tmem_base;
 };
 
@@ -274,7 +276,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(BT, 1) big_wgrad_kernel(const LinArgs a_in) {
+// kTma: the slabs are loaded by TMA (one extra warp; grouped 4-D maps, bbb_tma.cuh: one box = the 4 dz regions, one =
+// the 8 x regions of a stage, already in the MN-major layout), which streams them from L2 several times faster than
+// per-thread copies can (tools/wide_probe.cu); the 16 worker warps only touch a stage when it needs the ReLU or feeds
+// the bias column sums.  Needs in % 32 == 0 and out % 32 == 0; the cp.async variant covers every other shape.
+template <bool kTma>
+__global__ void __launch_bounds__(kTma ? BT + 32 : BT, 1)
+big_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x, const LinArgs a_in) {
   extern __shared__ uint8_t dsm[];
   __shared__ WCtl ctl;
   __shared__ float colsum_s[2][BM];     // sum_b dz[b][o] of the two samples in flight (bias gradients)
@@ -286,12 +294,14 @@ __global__ void __launch_bounds__(BT, 1) big_wgrad_kernel(const LinArgs a_in) {
   const bool bias_cta = blockIdx.y == 0;
   const int nkb = (int)((a.B + WKB - 1) / WKB);
   const int ngroups = (a.S + 1) / 2;
+  const bool need_fix = relu || bias_cta;      // (kTma) the worker warps pass over every stage before the MMAs read it
 
   if (warp == PW) tmem_alloc(smem_u32(&ctl.tmem_base), 512);
   if (tid == 0) {
 #pragma unroll
     for (int st = 0; st < WSTG; ++st) {
-      mbar_init(smem_u32(&ctl.full[st]), PW);
+      mbar_init(smem_u32(&ctl.full[st]), kTma ? 1 : PW);
+      mbar_init(smem_u32(&ctl.fixed[st]), PW);
       mbar_init(smem_u32(&ctl.empty[st]), 1);
     }
     mbar_init(smem_u32(&ctl.acc), 1);
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(BT, 1) big_wgrad_kernel(const LinArgs a_in) {
         for (int sl = 0; sl < ns; ++sl) {
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int st = it % WSTG;
-            mbar_wait_parked(smem_u32(&ctl.full[st]), (uint32_t)((it / WSTG) & 1));
+            mbar_wait_parked(smem_u32((kTma && need_fix) ? &ctl.fixed[st] : &ctl.full[st]), (uint32_t)((it / WSTG) & 1));
             tc_fence_after_sync();
             const uint32_t As = smem_u32(tiles + st * WSTAGE), Bs = As + WA_BYTES;
 #pragma unroll
@@ -334,6 +344,25 @@ __global__ void __launch_bounds__(BT, 1) big_wgrad_kernel(const LinArgs a_in) {
         tc_fence_after_sync();
       }
     }
+  } else if (kTma && warp == PW + 1) {
+    // ---- TMA warp: two boxes per stage, running ahead of the MMAs by up to WSTG stages (across samples and groups) ----
+    if (lane == 0) {
+      tma::prefetch_map(&tm_dz);
+      tma::prefetch_map(&tm_x);
+      int it = 0;
+      for (int s = 0; s < a.S; ++s) {
+        const int sx = a.x_sstride ? s : 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % WSTG;
+          if (it >= WSTG) mbar_wait(smem_u32(&ctl.empty[st]), (uint32_t)(((it / WSTG) - 1) & 1));
+          const uint32_t base = smem_u32(tiles + st * WSTAGE), bar = smem_u32(&ctl.full[st]);
+          tma::arrive_expect_tx(bar, (uint32_t)WSTAGE);
+          tma::load_4d(base, &tm_dz, bar, 0, kb * WKB, (int)(o0 >> 5), s);
+          tma::load_4d(base + WA_BYTES, &tm_x, bar, 0, kb * WKB, (int)(i0 >> 5), sx);
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ---- producers: slab copies.  dz: thread t -> batch rows t/32 + 16 h (h < 2), 16-byte chunk t%32 (4 o columns);
     //                              x : thread t -> batch rows t/64 + 8 h (h < 4),  16-byte chunk t%64 (4 i columns)
@@ -369,6 +398,35 @@ __global__ void __launch_bounds__(BT, 1) big_wgrad_kernel(const LinArgs a_in) {
           xoff[h] = WA_BYTES + b_off + mn32_off(br + 8 * h, bc & 7);
           xp[h] = xs + (int64_t)(br + 8 * h) * a.in;
         }
+        if constexpr (kTma) {
+          // the slabs arrive by TMA; this thread owns the same chunks of a stage as in the copying variant
+          if (need_fix) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+              const int st = it % WSTG;
+              mbar_wait(smem_u32(&ctl.full[st]), (uint32_t)((it / WSTG) & 1));
+              uint8_t *stage = tiles + st * WSTAGE;
+              if (bias_cta) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const float4 z = *reinterpret_cast<const float4 *>(stage + zoff[h]);
+                  bsum.x += z.x; bsum.y += z.y; bsum.z += z.z; bsum.w += z.w;
+                }
+              }
+              if (relu) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  float4 *px = reinterpret_cast<float4 *>(stage + xoff[h]);
+                  *px = relu4(*px);
+                }
+                fence_proxy_async_smem();
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive1(smem_u32(&ctl.fixed[st]));
+            }
+          } else {
+            it += nkb;
+          }
+        } else {
         const int64_t zstep = (int64_t)WKB * a.out, xstep = (int64_t)WKB * a.in;
         const uint32_t ring = smem_u32(tiles);
         auto issue_slab = [&](int kb, int j) {      // j: running stage index of that slab; called for kb = 0, 1, 2, ...
@@ -428,6 +486,7 @@ __global__ void __launch_bounds__(BT, 1) big_wgrad_kernel(const LinArgs a_in) {
           __syncwarp();
           if (lane == 0) mbar_arrive1(smem_u32(&ctl.full[st]));
         }
+        }   // !kTma
         if (bias_cta) {
           atomicAdd(&colsum_s[sl][ac * 4 + 0], bsum.x); atomicAdd(&colsum_s[sl][ac * 4 + 1], bsum.y);
           atomicAdd(&colsum_s[sl][ac * 4 + 2], bsum.z); atomicAdd(&colsum_s[sl][ac * 4 + 3], bsum.w);
@@ -548,9 +607,19 @@ bool linear_big_wgrad_supported(const LinArgs &a) {
   return a.vec_in && a.vec_out && a.B >= 384 && a.out >= 32 && a.in >= 32 && a.S >= 1 && !a.mask && !a.adam_on;
 }
 int launch_linear_wgrad_big(const LinArgs &a, cudaStream_t st) {
-  BBB_CHECK_CUDA(cudaFuncSetAttribute(big_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradDyn));
   dim3 grid(cdiv_i(a.out, BM), cdiv_i(a.in, WN));
-  BBB_CHECK_CUDA(launch_pdl(big_wgrad_kernel, grid, dim3(BT), kWgradDyn, st, a));
+  CUtensorMap tm_dz, tm_x;
+  if (a.in % 32 == 0 && a.out % 32 == 0) {
+    if (int r = tma::make_map_grouped(&tm_dz, a.dy, a.out, a.B, a.S, WKB, BM / 32, tma::kSw128Atom32)) return r;
+    if (int r = tma::make_map_grouped(&tm_x, a.x, a.in, a.B, a.x_sstride ? a.S : 1, WKB, WN / 32, tma::kSw128Atom32)) return r;
+    BBB_CHECK_CUDA(cudaFuncSetAttribute(big_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradDyn));
+    BBB_CHECK_CUDA(launch_pdl(big_wgrad_kernel<true>, grid, dim3(BT + 32), kWgradDyn, st, tm_dz, tm_x, a));
+  } else {
+    memset(&tm_dz, 0, sizeof(tm_dz));
+    memset(&tm_x, 0, sizeof(tm_x));
+    BBB_CHECK_CUDA(cudaFuncSetAttribute(big_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradDyn));
+    BBB_CHECK_CUDA(launch_pdl(big_wgrad_kernel<false>, grid, dim3(BT), kWgradDyn, st, tm_dz, tm_x, a));
+  }
   BBB_CHECK_LAUNCH();
   return BBB_OK;
 }

@@ -45,6 +45,34 @@ inline int make_map(CUtensorMap *map, const float *base, int64_t d0, int64_t d1,
   return BBB_OK;
 }
 
+// General form: `rank` dims (dims[0] contiguous), byte strides of dims 1.. (multiples of 16), box extents.
+inline int make_map_nd(CUtensorMap *map, const float *base, int rank, const int64_t *dims_in, const int64_t *strides_in,
+                       const int *box_in, Swz swz) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(BBB_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], es[5];
+  for (int i = 0; i < rank; ++i) { dims[i] = (cuuint64_t)dims_in[i]; box[i] = (cuuint32_t)box_in[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) strides[i] = (cuuint64_t)strides_in[i];
+  const CUtensorMapSwizzle sw = swz == kNone ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : swz == kSw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), dims, strides,
+                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BBB_ECUDA, "cuTensorMapEncodeTiled failed (%d) for a rank-%d map", (int)r, rank);
+  return BBB_OK;
+}
+// A row-major [S][rows][cols] matrix (cols % 32 == 0) seen as [S][cols / 32 groups][rows][32]: one box of
+// [1][groups][box_rows][32] lands as `groups` stacked [box_rows][128 B] regions -- with kSw128Atom32 the MN-major UMMA
+// operand slab of `groups * 32` columns, with kSw128 `groups` K-major tiles of 32 k each.
+inline int make_map_grouped(CUtensorMap *map, const float *base, int64_t cols, int64_t rows, int64_t S, int box_rows,
+                            int groups, Swz swz) {
+  const int64_t dims[4] = {32, rows, cols / 32, S > 0 ? S : 1};
+  const int64_t strides[3] = {cols * 4, 128, rows * cols * 4};
+  const int box[4] = {32, box_rows, groups, 1};
+  return make_map_nd(map, base, 4, dims, strides, box, swz);
+}
+
 // ---- device side ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_map(const CUtensorMap *m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
@@ -60,6 +88,10 @@ __device__ __forceinline__ void load_2d(uint32_t smem_dst, const CUtensorMap *m,
 __device__ __forceinline__ void load_3d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void load_4d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 // shared -> global reduction: every element of the [1][box1][box0] tile at `smem_src` is ADDED to the tensor (fp32 add
