@@ -38,12 +38,26 @@ extern "C" int bbb_linear_fwd(const float *x, int64_t x_sample_stride, const flo
   a.vec_in = (in % 4 == 0) && all16({x, w_mu, w_rho, eps_w});
   a.vec_out = (out % 4 == 0) && all16({y});
   cudaStream_t st = (cudaStream_t)stream;
+  const bool big = (flags & BBB_F_TF32) && !head_supported(a) && !linear_sk_supported(a) && linear_big_fwd_supported(a);
+  if ((flags & BBB_F_RELU_OUT) && !big)
+    return fail(BBB_EUNSUPPORTED, "BBB_F_RELU_OUT: only the large-batch tensor kernels store post-activations "
+                                  "(bbb_linear_fwd_relu_out_supported)");
   if (head_supported(a)) return launch_linear_fwd_head(a, st);                // out <= 16, both modes, exact fp32
   if ((flags & BBB_F_TF32) && linear_sk_supported(a)) return launch_linear_fwd_sk(a, st);
-  if ((flags & BBB_F_TF32) && linear_big_fwd_supported(a)) return launch_linear_fwd_big(a, st);   // batch >= 384
+  if (big)   // batch >= 384: TMA-fed, weight tiles shared in a cluster
+    return wide_disabled() ? launch_linear_fwd_big(a, st) : launch_linear_fwd_wide(a, st);
   if ((flags & BBB_F_TF32) && linear_tc_supported(a)) return launch_linear_fwd_tc(a, st);
   if (linear_narrow_supported(a)) return launch_linear_fwd_narrow(a, st);   // exact-fp32 mode, out <= 16
   return launch_linear_fwd_fma(a, st);
+}
+
+extern "C" int bbb_linear_fwd_relu_out_supported(int64_t B, int64_t in, int64_t out, int32_t flags) {
+  if (B <= 0 || in <= 0 || out <= 0) return 0;
+  LinArgs a{};
+  a.S = 1; a.B = B; a.in = in; a.out = out; a.flags = flags;
+  a.vec_in = in % 4 == 0;
+  a.vec_out = out % 4 == 0;
+  return ((flags & BBB_F_TF32) && !head_supported(a) && !linear_sk_supported(a) && linear_big_fwd_supported(a)) ? 1 : 0;
 }
 
 namespace {
@@ -58,7 +72,6 @@ int linear_bwd_impl(const float *dy, const float *dy_mask_src, const float *x, i
   BBB_CHECK_ARG((flags & BBB_F_NO_WGRAD) || adam || (grad_w_mu && grad_w_rho && grad_b_mu && grad_b_rho),
                 "null gradient pointer");
   BBB_CHECK_ARG((flags & BBB_F_NO_DX) || dx || S * B == 0, "dx required unless BBB_F_NO_DX");
-  BBB_CHECK_ARG(!(flags & BBB_F_DX_PREACT) || (flags & BBB_F_RELU_IN), "BBB_F_DX_PREACT needs BBB_F_RELU_IN");
   BBB_CHECK_ARG(S >= 0 && B >= 0 && in >= 0 && out >= 0 && S <= 65535, "bad shape");
   BBB_CHECK_ARG(x_sample_stride == 0 || x_sample_stride == B * in, "x_sample_stride must be 0 or B*in");
   const bool sample = flags & BBB_F_SAMPLE;
@@ -101,7 +114,7 @@ int linear_bwd_impl(const float *dy, const float *dy_mask_src, const float *x, i
     // goes to the batch-tiled kernels
     LinArgs rest = a;
     if (a.S > 0 && !(flags & BBB_F_NO_DX) && linear_big_dgrad_supported(a)) {
-      if (int r = launch_linear_dgrad_big(a, st)) return r;
+      if (int r = wide_disabled() ? launch_linear_dgrad_big(a, st) : launch_linear_dgrad_wide(a, st)) return r;
       rest.flags |= BBB_F_NO_DX;
     }
     if (a.S > 0 && !(flags & BBB_F_NO_WGRAD) && linear_big_wgrad_supported(a)) {

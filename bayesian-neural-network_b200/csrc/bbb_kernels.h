@@ -78,6 +78,11 @@ bool linear_big_fwd_supported(const LinArgs &a);
 bool linear_big_dgrad_supported(const LinArgs &a);
 int launch_linear_fwd_big(const LinArgs &a, cudaStream_t st);
 int launch_linear_dgrad_big(const LinArgs &a, cudaStream_t st);
+// second generation of the two (bbb_wide.cu): activation tiles by TMA, sampled weight tiles shared by the CTAs of a
+// cluster; same support conditions.  BBB_NO_WIDE=1 in the environment selects the first generation (A/B measurements).
+int launch_linear_fwd_wide(const LinArgs &a, cudaStream_t st);
+int launch_linear_dgrad_wide(const LinArgs &a, cudaStream_t st);
+bool wide_disabled();
 bool linear_big_wgrad_supported(const LinArgs &a);
 int launch_linear_wgrad_big(const LinArgs &a, cudaStream_t st);   // plain MN-major GEMM over the batch + sampling epilogue
 

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(BT, 1) big_kernel(const LinArgs a_in) {
       if (lpcta && cq == 0) { lp += logp_elem(a.prior, bias); lq += logq_elem(sg, ep); }
     }
     const float osc = (kDgrad && (a.flags & BBB_F_SCALE_DX) && a.out_scale_dev) ? __ldg(a.out_scale_dev) : 1.0f;
-    const bool preact = kDgrad && (a.flags & BBB_F_DX_PREACT);
+    const bool preact = kDgrad && (a.flags & BBB_F_DX_PREACT), relu_out = !kDgrad && (a.flags & BBB_F_RELU_OUT);
     float *dst = kDgrad ? a.dx + (int64_t)s * a.B * a.in : a.y + (int64_t)s * a.B * a.out;
     const float *msk = preact ? a.x + (int64_t)s * a.x_sstride : nullptr;
 #pragma unroll 1
@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(BT, 1) big_kernel(const LinArgs a_in) {
           const int64_t b = n0 + col + j;
           if (b < a.B) {
             float r = kDgrad ? osc * v[j] : v[j] + bias;
+            if (relu_out) r = fmaxf(r, 0.0f);
             if (preact && !(__ldg(msk + b * Mdim + m) > 0.0f)) r = 0.0f;
             dst[b * Mdim + m] = r;
           }

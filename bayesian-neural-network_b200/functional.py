@@ -225,11 +225,31 @@ def _workspace(shapes, device, zero):
     return [torch.empty(sh, dtype=torch.float32, device=device) for sh in shapes]
 
 
+_relu_out_cache = {}
+
+
+def _relu_out_layers(params, B, tf32):
+    """Per layer: is its output stored POST-activation (BBB_F_RELU_OUT)?  The large-batch tensor kernels do that for
+    hidden layers, so that nothing downstream passes over TMA-landed tiles to apply the ReLU; the consumers of such an
+    output are called without BBB_F_RELU_IN (the (x > 0) mask of BBB_F_DX_PREACT is the same on either form)."""
+    if not tf32:
+        return [False] * len(params)
+    key = (B, tuple(tuple(p[0].shape) for p in params))
+    ro = _relu_out_cache.get(key)
+    if ro is None:
+        ro = [l < len(params) - 1 and
+              bool(L.lib().bbb_linear_fwd_relu_out_supported(B, p[0].shape[1], p[0].shape[0], L.F_TF32))
+              for l, p in enumerate(params)]
+        _relu_out_cache[key] = ro
+    return ro
+
+
 def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq, ys=None, head=None):
-    """All layers, all S samples.  Returns the list of pre-activation outputs ys[l] = [S,B,out_l]
-    (written into the zero-filled `ys` when the caller supplies them).  `head(inp, stride, flags, y)`, when given,
-    runs the last layer instead of bbb_linear_fwd (the fused ELBO tail)."""
+    """All layers, all S samples.  Returns the list of outputs ys[l] = [S,B,out_l]: pre-activations, except the hidden
+    layers _relu_out_layers names (written into the zero-filled `ys` when the caller supplies them).
+    `head(inp, stride, flags, y)`, when given, runs the last layer instead of bbb_linear_fwd (the fused ELBO tail)."""
     B = x2.shape[0]
+    ro = _relu_out_layers(params, B, tf32)
     base = ((L.F_SAMPLE if sample else 0) | (L.F_LOGPROB if logprob else 0) | (L.F_TF32 if tf32 else 0) |
             (L.F_OUT_ZEROED if _prezero(B) else 0))
     if ys is None:
@@ -237,7 +257,7 @@ def _net_ws_forward(x2, params, prior, S, eps, sample, logprob, tf32, logp, logq
     inp, stride = x2, 0
     for l, p in enumerate(params):
         out, inn = p[0].shape
-        flags = base | (L.F_RELU_IN if l > 0 else 0)
+        flags = base | (L.F_RELU_IN if l > 0 and not ro[l - 1] else 0) | (L.F_RELU_OUT if ro[l] else 0)
         if head is not None and l == len(params) - 1:
             head(inp, stride, flags, ys[l])
         else:
@@ -252,6 +272,7 @@ def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq,
     hands down the gradient w.r.t. the PRE-activation output of the layer below (BBB_F_DX_PREACT: the ReLU mask
     is applied where dx is produced), so no layer needs a separate mask pass over dy."""
     B = x2.shape[0]
+    ro = _relu_out_layers(params, B, tf32)
     base = (L.F_SAMPLE if sample else 0) | (L.F_TF32 if tf32 else 0) | (L.F_OUT_ZEROED if _prezero(B) else 0)
     grads = _alloc_grads(params) if fused_opt is None else [None] * len(params)
     dy, dx0 = d_out, None
@@ -262,7 +283,7 @@ def _net_ws_backward(x2, ys, d_out, params, prior, S, eps, sample, tf32, gp, gq,
         p = params[l]
         out, inn = p[0].shape
         g = grads[l]
-        flags = base | ((L.F_RELU_IN | L.F_DX_PREACT) if l > 0 else 0)
+        flags = base | (L.F_DX_PREACT if l > 0 else 0) | (L.F_RELU_IN if l > 0 and not ro[l - 1] else 0)
         want_dx = l > 0 or need_dx0
         dx = dxs[l] if want_dx else None
         if not want_dx:

@@ -51,8 +51,14 @@ extern "C" {
 #define BBB_F_NO_DX 32     /* backward: do not compute dx                                      */
 #define BBB_F_SCALE_DX 64  /* backward: out_scale_dev also multiplies dx                       */
 #define BBB_F_NO_WGRAD 128 /* backward: do not compute parameter gradients (dx only)           */
-#define BBB_F_DX_PREACT 512 /* backward, with BBB_F_RELU_IN: dx is multiplied by (x > 0), i.e. it is the gradient
+#define BBB_F_DX_PREACT 512 /* backward: dx is multiplied by (x > 0) (x the stored input: a pre-activation with
+                               BBB_F_RELU_IN, the post-activation itself without it), i.e. it is the gradient
                               w.r.t. the PRE-activation input; the layer below then needs no dy_mask_src      */
+#define BBB_F_RELU_OUT 1024 /* forward: store max(y, 0) instead of y.  The consumers of such an output are then called
+                               WITHOUT BBB_F_RELU_IN (BBB_F_DX_PREACT still masks by (x > 0), which is the same mask), so
+                               no kernel spends shared-memory bandwidth on a ReLU pass over TMA-landed tiles.  Implemented
+                               by the large-batch tensor kernels only: ask bbb_linear_fwd_relu_out_supported first; a
+                               call that sets it on any other path returns BBB_EUNSUPPORTED. */
 #define BBB_F_OUT_ZEROED 256 /* y (forward) / dx (backward) is already zero-filled by the caller: kernels that
                                combine split-K partial sums with red.add skip their own memset              */
 
@@ -89,6 +95,8 @@ int bbb_linear_fwd(const float *x, int64_t x_sample_stride, const float *w_mu, c
                    const float *b_mu, const float *b_rho, const float *eps_w, const float *eps_b,
                    const bbb_rng *rng, const bbb_prior *prior, int64_t S, int64_t B, int64_t in,
                    int64_t out, int32_t flags, float *y, double *logp, double *logq, void *stream);
+/* 1 when bbb_linear_fwd honours BBB_F_RELU_OUT for this shape and `flags` (16-byte aligned pointers assumed) */
+int bbb_linear_fwd_relu_out_supported(int64_t B, int64_t in, int64_t out, int32_t flags);
 
 /* replaces the autograd backward of the above (triggered at reg_task.py:72, class_task.py:78,
  * bandits.py:49).  With t = dy^T x - gp w R(w):  grad_mu = sum_s t,  grad_rho = sum_s

@@ -14,7 +14,7 @@ import numpy as np
 from oracle import closed_form as CF
 
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
-F_OUT_ZEROED, F_DX_PREACT = 256, 512
+F_OUT_ZEROED, F_DX_PREACT, F_RELU_OUT = 256, 512, 1024
 
 
 def _arr(ptr, ctype, *shape):
@@ -73,10 +73,16 @@ class FakeLib:
             w = WM + sw * e_w if sample else WM
             b = BM + sb * e_b if sample else BM
             Y[s] = (xs_ @ w.T + b).astype(np.float32)
+            if flags & F_RELU_OUT:
+                Y[s] = np.maximum(Y[s], 0)
             if lpq:
                 LP[s] += CF.prior_terms(w, pr)[0] + CF.prior_terms(b, pr)[0]
                 LQ[s] += CF.log_q(sw, e_w) + CF.log_q(sb, e_b)
         return 0
+
+    def bbb_linear_fwd_relu_out_supported(self, B, inn, out, flags):
+        # as the library: TF32 mode, batches of >= 384 rows, 16-byte rows, not a head-sized layer
+        return int(bool(flags & 16) and B >= 384 and inn % 4 == 0 and inn >= 32 and out >= 32)
 
     def bbb_linear_bwd(self, dy, mask, x, xs, wm, wr, bm, br, ew, eb, rng, prior, S, B, inn, out, flags, gp, gq,
                        gp_dev, gq_dev, gstride, oscale, dx, gwm, gwr, gbm, gbr, st):
@@ -116,8 +122,7 @@ class FakeLib:
             a_br += CF.sigmoid(BR) * (tb * e_b - gqs / sb)
             if DX is not None:
                 d = (dz @ w) * (osc if flags & F_SCALE_DX else 1.0)
-                if flags & F_DX_PREACT:
-                    assert relu
+                if flags & F_DX_PREACT:      # x_pre: the stored input, pre- (with F_RELU_IN) or post-activation
                     d = d * (x_pre > 0)
                 DX[s] = d.astype(np.float32)
         for ptr, shape, val in ((gwm, (out, inn), a_wm), (gwr, (out, inn), a_wr), (gbm, (out,), a_bm),

@@ -202,6 +202,33 @@ def test_fused_step_above_128_rows_uses_uninitialised_workspace(fake):
             assert (p.grad - q.grad).abs().max() <= 2e-5 * q.grad.abs().max() + 1e-7
 
 
+def test_large_batch_tf32_step_stores_post_activations(fake):
+    """TF32 mode, >= 384 rows: the hidden layers the library can do it for are asked to store max(y, 0)
+    (BBB_F_RELU_OUT) and their consumers -- next forward, wgrad, the (x > 0) mask of dgrad, the head -- are called
+    without BBB_F_RELU_IN; the step still equals the oracle's."""
+    from bnn_b200 import functional as F
+    from oracle import bbb_oracle as O
+    torch.manual_seed(4)
+    dims, B, S = (32, 40, 36, 4), 400, 2
+    layers = O.init_layers(dims, [-0.2, 0.2], [-5, -4])
+    x, y = torch.randn(B, dims[0]), torch.randint(0, dims[-1], (B,))
+    eps = O.draw_eps(dims, S)
+    ref = [tuple(p.clone().requires_grad_(True) for p in layer) for layer in layers]
+    want = O.train_step(x, y, ref, O.make_prior([0.5, 0, -6], True), eps, 0.4, 'classification', 1.0)
+    mine = [tuple(p.clone().requires_grad_(True) for p in layer) for layer in layers]
+    assert F._relu_out_layers(mine, B, True) == [True, True, False] and not any(F._relu_out_layers(mine, B, False))
+    assert F._relu_out_layers(mine, 128, True) == [False] * 3
+    bnn_b200.rng.set_injected_eps([t for per in eps for pair in per for t in pair])
+    with bnn_b200.eps_mode('injected'):
+        got = F.fused_elbo(x, y, 0.4, S, 1.0, 'classification', F.make_prior([0.5, 0, -6], True), mine, tf32=True)
+    got[0].backward()
+    for a, b in zip(got, want):
+        assert abs(float(a.detach().reshape(-1)[0]) - float(b.detach().reshape(-1)[0])) <= 1e-5 * abs(float(b.detach().reshape(-1)[0])) + 1e-6
+    for la, lb in zip(mine, ref):
+        for p, q in zip(la, lb):
+            assert (p.grad - q.grad).abs().max() <= 2e-5 * q.grad.abs().max() + 1e-7
+
+
 def test_beta_may_be_a_tensor(fake):
     c = Case('small_cls_mix')
     outs = []

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """CUDA-event timings of the batch-resident (wide-layer) kernels through the C ABI: forward, dgrad and wgrad of one
-hidden layer, with the GEMM rate each reaches.  Also checks the three against a float64 torch restatement (mean weights,
+hidden layer, with the GEMM rate each reaches ('post': the input is a stored post-activation, no ReLU on load; 'nolp':
+without the log-prob terms).  Also checks the three against a float64 torch restatement (mean weights,
 sample=False) so that a change to them is verified and timed in one GPU call.
 usage: python tools/time_wide.py [width=4096] [B=4096] [S=2]"""
 import ctypes as C
@@ -32,16 +33,16 @@ st = torch.cuda.current_stream().cuda_stream
 xs = B * inn
 
 
-def fwd(flags=L.F_SAMPLE | L.F_LOGPROB):
+def fwd(flags=L.F_SAMPLE | L.F_LOGPROB, relu=L.F_RELU_IN):
     L.check(L.lib().bbb_linear_fwd(x.data_ptr(), xs, wm.data_ptr(), wr.data_ptr(), bm.data_ptr(), br.data_ptr(), None,
-                                   None, C.byref(rng), C.byref(prior), S, B, inn, out, L.F_TF32 | L.F_RELU_IN | flags,
+                                   None, C.byref(rng), C.byref(prior), S, B, inn, out, L.F_TF32 | relu | flags,
                                    y.data_ptr(), acc[:S].data_ptr(), acc[S:].data_ptr(), st), 'fwd')
 
 
-def bwd(extra, flags=L.F_SAMPLE, gp=-0.25, gq=0.25):
+def bwd(extra, flags=L.F_SAMPLE, gp=-0.25, gq=0.25, relu=L.F_RELU_IN):
     L.check(L.lib().bbb_linear_bwd(dy.data_ptr(), None, x.data_ptr(), xs, wm.data_ptr(), wr.data_ptr(), bm.data_ptr(),
                                    br.data_ptr(), None, None, C.byref(rng), C.byref(prior), S, B, inn, out,
-                                   L.F_TF32 | L.F_RELU_IN | L.F_DX_PREACT | flags | extra, gp, gq, None, None, 0, None,
+                                   L.F_TF32 | relu | L.F_DX_PREACT | flags | extra, gp, gq, None, None, 0, None,
                                    dx.data_ptr(), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), st),
             'bwd')
 
@@ -81,6 +82,9 @@ print(f'grad_w_mu err {e_g:.2e}  grad_b_mu err {e_gb:.2e}  ->', 'OK' if ok else 
 
 # ---- time ---------------------------------------------------------------------------------------------------------
 flops = 2.0 * S * B * inn * out
-for name, fn in (('forward', fwd), ('dgrad', lambda: bwd(L.F_NO_WGRAD)), ('wgrad', lambda: bwd(L.F_NO_DX))):
+RO = getattr(L, 'F_RELU_OUT', 0)
+for name, fn in (('forward', fwd), ('fwd post', lambda: fwd(L.F_SAMPLE | L.F_LOGPROB | RO, 0)),
+                 ('fwd nolp', lambda: fwd(L.F_SAMPLE | RO, 0)), ('dgrad', lambda: bwd(L.F_NO_WGRAD)),
+                 ('wgrad', lambda: bwd(L.F_NO_DX)), ('wgr post', lambda: bwd(L.F_NO_DX, relu=0))):
     us = timeit(fn)
     print(f'{name:8s} [{inn}x{out}] B={B} S={S}: {us:8.1f} us = {us / S:7.1f} us/sample, {flops / us / 1e6:6.1f} TFLOP/s', flush=True)
