@@ -507,44 +507,61 @@ big_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
       const int q4 = warp & 3, cq = warp >> 2;
       const int64_t o = o0 + q4 * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < 64; c0 += 8) {
         const int col = cq * 64 + c0;
         if (i0 + col >= a.in) break;                       // warp-uniform
-        float G[2][16];
-        tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, G[0]);
-        if (ns > 1) tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(WN + col), G[1]);
-        if (o < a.out) {
+        // two quads at a time, every load of the pair (mu, rho, the running gradient sums) issued before the accumulators
+        // are read and before the first store: interleaved with the stores they would go out one L2 round trip at a
+        // time (possible aliasing).  (tcgen05.ld is warp-collective: rows past `out` take part with their loads clamped.)
+        const bool o_ok = o < a.out;
+        float4 m4[2], r4[2], om[2], orr[2];
+        bool ok[2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t i = i0 + col + 4 * j;
-            if (i < a.in) {
-              const int64_t e = o * a.in + i;
-              Quad q;
-              load_quad(a, e, true, q);
-              float gm[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int u = 0; u < 2; ++u) {
+          const int64_t i = i0 + col + 4 * u;
+          ok[u] = o_ok && i < a.in;
+          const int64_t e = ok[u] ? o * a.in + i : 0;
+          m4[u] = __ldg(reinterpret_cast<const float4 *>(a.w_mu + e));
+          r4[u] = __ldg(reinterpret_cast<const float4 *>(a.w_rho + e));
+          om[u] = orr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (accum && ok[u]) {
+            om[u] = *reinterpret_cast<const float4 *>(a.g_w_mu + e);
+            orr[u] = *reinterpret_cast<const float4 *>(a.g_w_rho + e);
+          }
+        }
+        float G[2][8];
+        tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, G[0]);
+        if (ns > 1) tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(WN + col), G[1]);
 #pragma unroll
-              for (int sl = 0; sl < 2; ++sl) {
-                if (sl < ns) {
-                  float ep[4], w[4];
-                  sample_quad(a, s0 + sl, e, q, sample, ep, w);
+        for (int u = 0; u < 2; ++u) {
+          if (!ok[u]) continue;
+          const int64_t e = o * a.in + i0 + col + 4 * u;
+          Quad q;
+          q.mu[0] = m4[u].x; q.mu[1] = m4[u].y; q.mu[2] = m4[u].z; q.mu[3] = m4[u].w;
+          q.rho[0] = r4[u].x; q.rho[1] = r4[u].y; q.rho[2] = r4[u].z; q.rho[3] = r4[u].w;
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) {
-                    float t = G[sl][4 * j + c];
-                    if (gps[sl] != 0.0f) t = fmaf(-gps[sl] * w[c], prior_R_fast(a.prior, w[c]), t);
-                    gm[c] += t;
-                    gr[c] += t * ep[c] - gqs[sl] * __fdividef(1.0f, q.sg[c]);
-                  }
-                }
+          for (int c = 0; c < 4; ++c) q.sg[c] = softplus_fast(q.rho[c]);
+          float gm[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            if (sl < ns) {
+              float ep[4], w[4];
+              sample_quad(a, s0 + sl, e, q, sample, ep, w);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float t = G[sl][4 * u + c];
+                if (gps[sl] != 0.0f) t = fmaf(-gps[sl] * w[c], prior_R_fast(a.prior, w[c]), t);
+                gm[c] += t;
+                gr[c] += t * ep[c] - gqs[sl] * __fdividef(1.0f, q.sg[c]);
               }
-#pragma unroll
-              for (int c = 0; c < 4; ++c) gr[c] *= sigmoid_fast(q.rho[c]);
-              float4 *pm = reinterpret_cast<float4 *>(a.g_w_mu + e), *pr = reinterpret_cast<float4 *>(a.g_w_rho + e);
-              float4 om = make_float4(0.f, 0.f, 0.f, 0.f), orr = om;
-              if (accum) { om = *pm; orr = *pr; }
-              *pm = make_float4(fmaf(osc, gm[0], om.x), fmaf(osc, gm[1], om.y), fmaf(osc, gm[2], om.z), fmaf(osc, gm[3], om.w));
-              *pr = make_float4(fmaf(osc, gr[0], orr.x), fmaf(osc, gr[1], orr.y), fmaf(osc, gr[2], orr.z), fmaf(osc, gr[3], orr.w));
             }
           }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) gr[c] *= sigmoid_fast(q.rho[c]);
+          *reinterpret_cast<float4 *>(a.g_w_mu + e) = make_float4(fmaf(osc, gm[0], om[u].x), fmaf(osc, gm[1], om[u].y),
+                                                                  fmaf(osc, gm[2], om[u].z), fmaf(osc, gm[3], om[u].w));
+          *reinterpret_cast<float4 *>(a.g_w_rho + e) = make_float4(fmaf(osc, gr[0], orr[u].x), fmaf(osc, gr[1], orr[u].y),
+                                                                   fmaf(osc, gr[2], orr[u].z), fmaf(osc, gr[3], orr[u].w));
         }
       }
       // bias gradients: column sums of dz, by the CTAs of the first i tile

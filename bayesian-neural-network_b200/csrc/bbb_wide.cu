@@ -272,6 +272,16 @@ __global__ void __launch_bounds__(WT, 1) wide_kernel(const __grid_constant__ CUt
     for (int c0 = 0; c0 < 128; c0 += 32) {
       const int col = cq * 128 + c0;
       if (n0 + col >= a.B) break;                 // warp-uniform: the rest of this warp's columns are past the batch
+      // the (x > 0) mask of these 32 batch columns first, all loads in flight at once (`dst` may alias nothing here, but
+      // the compiler cannot know: interleaved with the stores they would be issued one L2 round trip at a time)
+      float mk[32];
+      if (preact) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int64_t b = min(n0 + col + j, a.B - 1);
+          mk[j] = m_ok ? __ldg(msk + b * Mdim + m) : 0.0f;
+        }
+      }
       float v[32];
       tmem_ld32w(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);
       if (m_ok) {
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(WT, 1) wide_kernel(const __grid_constant__ CUt
           if (b < a.B) {
             float r = kDgrad ? osc * v[j] : v[j] + bias;
             if (relu_out) r = fmaxf(r, 0.0f);
-            if (preact && !(__ldg(msk + b * Mdim + m) > 0.0f)) r = 0.0f;
+            if (preact && !(mk[j] > 0.0f)) r = 0.0f;
             dst[b * Mdim + m] = r;
           }
         }
@@ -347,8 +357,9 @@ int launch_wide(const LinArgs &a, cudaStream_t st) {
   }
   const int n_bt = cdiv_w(a.B, NBT);
   dim3 grid(cdiv_w(kDgrad ? a.in : a.out, BM), n_bt, (unsigned)a.S);
-  if (n_bt % 4 == 0) return launch_wide_cl<kDgrad, kLogProb, 4>(tm, a, grid, st);
-  if (n_bt % 2 == 0) return launch_wide_cl<kDgrad, kLogProb, 2>(tm, a, grid, st);
+  static const int max_cl = [] { const char *e = getenv("BBB_WIDE_CL"); return e ? atoi(e) : 4; }();   // (experiments)
+  if (n_bt % 4 == 0 && max_cl >= 4) return launch_wide_cl<kDgrad, kLogProb, 4>(tm, a, grid, st);
+  if (n_bt % 2 == 0 && max_cl >= 2) return launch_wide_cl<kDgrad, kLogProb, 2>(tm, a, grid, st);
   return launch_wide_cl<kDgrad, kLogProb, 1>(tm, a, grid, st);
 }
 

@@ -39,10 +39,10 @@ def fwd(flags=L.F_SAMPLE | L.F_LOGPROB, relu=L.F_RELU_IN):
                                    y.data_ptr(), acc[:S].data_ptr(), acc[S:].data_ptr(), st), 'fwd')
 
 
-def bwd(extra, flags=L.F_SAMPLE, gp=-0.25, gq=0.25, relu=L.F_RELU_IN):
+def bwd(extra, flags=L.F_SAMPLE, gp=-0.25, gq=0.25, relu=L.F_RELU_IN, pre=L.F_DX_PREACT):
     L.check(L.lib().bbb_linear_bwd(dy.data_ptr(), None, x.data_ptr(), xs, wm.data_ptr(), wr.data_ptr(), bm.data_ptr(),
                                    br.data_ptr(), None, None, C.byref(rng), C.byref(prior), S, B, inn, out,
-                                   L.F_TF32 | relu | L.F_DX_PREACT | flags | extra, gp, gq, None, None, 0, None,
+                                   L.F_TF32 | relu | pre | flags | extra, gp, gq, None, None, 0, None,
                                    dx.data_ptr(), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), st),
             'bwd')
 
@@ -84,7 +84,7 @@ print(f'grad_w_mu err {e_g:.2e}  grad_b_mu err {e_gb:.2e}  ->', 'OK' if ok else 
 flops = 2.0 * S * B * inn * out
 RO = getattr(L, 'F_RELU_OUT', 0)
 for name, fn in (('forward', fwd), ('fwd post', lambda: fwd(L.F_SAMPLE | L.F_LOGPROB | RO, 0)),
-                 ('fwd nolp', lambda: fwd(L.F_SAMPLE | RO, 0)), ('dgrad', lambda: bwd(L.F_NO_WGRAD)),
+                 ('fwd nolp', lambda: fwd(L.F_SAMPLE | RO, 0)), ('dgrad', lambda: bwd(L.F_NO_WGRAD)), ('dgr nomk', lambda: bwd(L.F_NO_WGRAD, relu=0, pre=0)),
                  ('wgrad', lambda: bwd(L.F_NO_DX)), ('wgr post', lambda: bwd(L.F_NO_DX, relu=0))):
     us = timeit(fn)
     print(f'{name:8s} [{inn}x{out}] B={B} S={S}: {us:8.1f} us = {us / S:7.1f} us/sample, {flops / us / 1e6:6.1f} TFLOP/s', flush=True)
