@@ -80,6 +80,7 @@ _SIGS = {
     'bbb_counter_add': ([P, U32, P], C.c_int),
     'bbb_timing_enable': ([I32], C.c_int),
     'bbb_debug_set_timeline': ([P], C.c_int),
+    'bbb_debug_wgrad_split': ([C.c_int], C.c_int),
     'bbb_timing_report': ([C.c_char_p, I64], C.c_int),
 }
 EXPORTS = tuple(_SIGS)

@@ -20,6 +20,8 @@
 // W never leaves the SM; eps is regenerated from the same Philox coordinates in the backward.
 #include "bbb_tc_tiles.cuh"
 #include "bbb_tma.cuh"
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace bbb {
@@ -263,6 +265,12 @@ struct WCtl {
   uint64_t full[WSTG], fixed[WSTG], empty[WSTG], acc;
   uint32_t tmem_base;
 };
+// gridDim.z = 2 splits the sample groups of every tile over two CTAs (the 512 tiles of a 4096 x 4096 layer fill 3.46
+// waves of 148 SMs, 1024 half-jobs fill 6.92): z = 0 writes the gradient tensors, z = 1 these partial tensors, which
+// wgrad_combine_kernel adds in afterwards (two addends: the sum does not depend on any order)
+struct WgradPart {
+  float *w_mu, *w_rho, *b_mu, *b_rho;
+};
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   uint32_t r[16];
@@ -283,18 +291,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 // the bias column sums.  Needs in % 32 == 0 and out % 32 == 0; the cp.async variant covers every other shape.
 template <bool kTma>
 __global__ void __launch_bounds__(kTma ? BT + 32 : BT, 1)
-big_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x, const LinArgs a_in) {
+big_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x, const LinArgs a_in,
+                 const WgradPart part) {
   extern __shared__ uint8_t dsm[];
   __shared__ WCtl ctl;
   __shared__ float colsum_s[2][BM];     // sum_b dz[b][o] of the two samples in flight (bias gradients)
   LinArgs a = a_in;
   uint8_t *tiles = align1024(dsm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN, accum_flag = a.flags & BBB_F_ACCUM;
+  const bool sample = a.flags & BBB_F_SAMPLE, relu = a.flags & BBB_F_RELU_IN;
+  bool accum_flag = a.flags & BBB_F_ACCUM;
   const int64_t o0 = (int64_t)blockIdx.x * BM, i0 = (int64_t)blockIdx.y * WN;
   const bool bias_cta = blockIdx.y == 0;
   const int nkb = (int)((a.B + WKB - 1) / WKB);
-  const int ngroups = (a.S + 1) / 2;
+  // this CTA's share of the sample groups: groups [g_lo, g_hi) = samples [s_base, s_base + S_loc)
+  const int ngroups_all = (a.S + 1) / 2;
+  const int g_lo = ngroups_all * (int)blockIdx.z / (int)gridDim.z, g_hi = ngroups_all * ((int)blockIdx.z + 1) / (int)gridDim.z;
+  const int s_base = 2 * g_lo, S_loc = min(a.S, 2 * g_hi) - s_base, ngroups = g_hi - g_lo;
+  if (blockIdx.z > 0) {
+    a.g_w_mu = part.w_mu; a.g_w_rho = part.w_rho; a.g_b_mu = part.b_mu; a.g_b_rho = part.b_rho;
+    accum_flag = false;
+  }
   const bool need_fix = relu || bias_cta;      // (kTma) the worker warps pass over every stage before the MMAs read it
 
   if (warp == PW) tmem_alloc(smem_u32(&ctl.tmem_base), 512);
@@ -321,7 +338,7 @@ big_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
     constexpr uint32_t idesc = idesc_tf32_major(BM, WN, 1, 1);
     int it = 0;
     for (int g = 0; g < ngroups; ++g) {
-      const int ns = min(2, a.S - 2 * g);
+      const int ns = min(2, S_loc - 2 * g);
       if (lane == 0) {
         for (int sl = 0; sl < ns; ++sl) {
           for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -351,7 +368,7 @@ big_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
       tma::prefetch_map(&tm_dz);
       tma::prefetch_map(&tm_x);
       int it = 0;
-      for (int s = 0; s < a.S; ++s) {
+      for (int s = s_base; s < s_base + S_loc; ++s) {
         const int sx = a.x_sstride ? s : 0;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int st = it % WSTG;
@@ -373,7 +390,7 @@ big_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constan
     const bool ao_ok = ao < a.out, bi_ok = bi < a.in;
     int it = 0;
     for (int g = 0; g < ngroups; ++g) {
-      const int s0 = 2 * g, ns = min(2, a.S - s0);
+      const int s0 = s_base + 2 * g, ns = min(2, S_loc - 2 * g);
       if (bias_cta && tid < 2 * BM) colsum_s[tid >> 7][tid & (BM - 1)] = 0.0f;
       for (int sl = 0; sl < ns; ++sl) {
         const float *dzs = a.dy + (int64_t)(s0 + sl) * a.B * a.out + (ao_ok ? ao : 0);
@@ -624,21 +641,78 @@ int launch_linear_dgrad_big(const LinArgs &a, cudaStream_t st) { return launch_b
 bool linear_big_wgrad_supported(const LinArgs &a) {
   return a.vec_in && a.vec_out && a.B >= 384 && a.out >= 32 && a.in >= 32 && a.S >= 1 && !a.mask && !a.adam_on;
 }
+namespace {
+// g += p for the four gradient tensors (float4 where the weight matrices allow it: in % 4 == 0 on this path)
+__global__ void __launch_bounds__(256) wgrad_combine_kernel(float *g_w_mu, float *g_w_rho, float *g_b_mu, float *g_b_rho,
+                                                            const WgradPart p, int64_t n_w4, int64_t n_b) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_w4; i += stride) {
+    float4 a = reinterpret_cast<float4 *>(g_w_mu)[i], b = reinterpret_cast<const float4 *>(p.w_mu)[i];
+    reinterpret_cast<float4 *>(g_w_mu)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    a = reinterpret_cast<float4 *>(g_w_rho)[i]; b = reinterpret_cast<const float4 *>(p.w_rho)[i];
+    reinterpret_cast<float4 *>(g_w_rho)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_b; i += stride) {
+    g_b_mu[i] += p.b_mu[i];
+    g_b_rho[i] += p.b_rho[i];
+  }
+}
+}  // namespace
+
+static int g_wgrad_split_mode = 0;
+extern "C" int bbb_debug_wgrad_split(int mode) {
+  g_wgrad_split_mode = mode;
+  return BBB_OK;
+}
+
 int launch_linear_wgrad_big(const LinArgs &a, cudaStream_t st) {
   dim3 grid(cdiv_i(a.out, BM), cdiv_i(a.in, WN));
+  // Split the sample groups of every tile over two CTAs when that fills the SMs better (see WgradPart)
+  const int ngroups = (a.S + 1) / 2;
+  const double waves = (double)grid.x * grid.y / sm_count();
+  const double eff1 = waves / ceil(waves), eff2 = 2 * waves / ceil(2 * waves);
+  const int mode = g_wgrad_split_mode;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  BBB_CHECK_CUDA(cudaStreamIsCapturing(st, &cap));      // (no workspace allocation inside a graph capture)
+  const bool split = ngroups >= 2 && mode >= 0 && (mode > 0 || eff2 > eff1 + 0.03) && cap == cudaStreamCaptureStatusNone;
+  WgradPart part{};
+  float *wsp = nullptr;
+  const int64_t n_w = a.in * a.out, n_b4 = (a.out + 3) / 4 * 4;
+  if (split) {
+    grid.z = 2;
+    // stream-ordered workspace from the device's default pool; the pool keeps what it is given back (without a release
+    // threshold it would return the memory to the driver at every synchronisation and re-map it on the next call)
+    static bool pool_set[64] = {false};
+    int dev = 0;
+    BBB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+      cudaMemPool_t pool;
+      BBB_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+      uint64_t keep = UINT64_MAX;
+      BBB_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      pool_set[dev] = true;
+    }
+    BBB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&wsp), (size_t)(2 * n_w + 2 * n_b4) * sizeof(float), st));
+    part.w_mu = wsp; part.w_rho = wsp + n_w; part.b_mu = wsp + 2 * n_w; part.b_rho = wsp + 2 * n_w + n_b4;
+  }
   CUtensorMap tm_dz, tm_x;
   if (a.in % 32 == 0 && a.out % 32 == 0) {
     if (int r = tma::make_map_grouped(&tm_dz, a.dy, a.out, a.B, a.S, WKB, BM / 32, tma::kSw128Atom32)) return r;
     if (int r = tma::make_map_grouped(&tm_x, a.x, a.in, a.B, a.x_sstride ? a.S : 1, WKB, WN / 32, tma::kSw128Atom32)) return r;
     BBB_CHECK_CUDA(cudaFuncSetAttribute(big_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradDyn));
-    BBB_CHECK_CUDA(launch_pdl(big_wgrad_kernel<true>, grid, dim3(BT + 32), kWgradDyn, st, tm_dz, tm_x, a));
+    BBB_CHECK_CUDA(launch_pdl(big_wgrad_kernel<true>, grid, dim3(BT + 32), kWgradDyn, st, tm_dz, tm_x, a, part));
   } else {
     memset(&tm_dz, 0, sizeof(tm_dz));
     memset(&tm_x, 0, sizeof(tm_x));
     BBB_CHECK_CUDA(cudaFuncSetAttribute(big_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradDyn));
-    BBB_CHECK_CUDA(launch_pdl(big_wgrad_kernel<false>, grid, dim3(BT), kWgradDyn, st, tm_dz, tm_x, a));
+    BBB_CHECK_CUDA(launch_pdl(big_wgrad_kernel<false>, grid, dim3(BT), kWgradDyn, st, tm_dz, tm_x, a, part));
   }
   BBB_CHECK_LAUNCH();
+  if (split) {
+    wgrad_combine_kernel<<<sm_count() * 4, 256, 0, st>>>(a.g_w_mu, a.g_w_rho, a.g_b_mu, a.g_b_rho, part, n_w / 4, a.out);
+    BBB_CHECK_LAUNCH();
+    BBB_CHECK_CUDA(cudaFreeAsync(wsp, st));
+  }
   return BBB_OK;
 }
 

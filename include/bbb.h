@@ -326,6 +326,10 @@ int bbb_timing_enable(int32_t on);
  * (phase boundaries, ns) at buf[2560 * launch + 16 * cta ..] (launch = 0..7, in launch order; buf holds 8 * 2560 words);
  * tools/kernel_timeline.py prints the phase durations.  NULL switches it off. */
 int bbb_debug_set_timeline(unsigned long long *buf);
+/* Debug / test aid: the large-batch wgrad splits the sample groups of a tile over two CTAs (partial gradients in a
+ * stream-ordered workspace, added in by a second kernel) when that fills the SMs better.  mode 0: decide by shape
+ * (default), 1: split whenever there are two sample groups, -1: never. */
+int bbb_debug_wgrad_split(int mode);
 int bbb_timing_report(char *buf, int64_t buf_bytes);
 
 /* *counter += inc  (advances a bbb_rng.step_dev between steps; one tiny launch, graph-capturable) */

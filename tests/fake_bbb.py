@@ -427,6 +427,9 @@ class FakeLib:
     def bbb_timing_enable(self, on):
         return 0
 
+    def bbb_debug_wgrad_split(self, mode):
+        return 0
+
     def bbb_debug_set_timeline(self, buf):
         return 0
 

@@ -111,8 +111,24 @@ def test_batch_resident_plain_gemm(B, d_in, d_out):
     assert err < 2e-3, float(err)
 
 
-@pytest.mark.parametrize('B,d_in,hidden,S', [(400, 64, 96, 3), (1024, 128, 160, 2), (600, 36, 200, 1)])
-def test_batch_resident_train_step_matches_fp32_path(B, d_in, hidden, S):
+@pytest.fixture(params=[0, 1], ids=['auto', 'wgrad-split'])
+def wgrad_split(request):
+    """1: force the large-batch wgrad to split a tile's sample groups over two CTAs (partial gradients + combine kernel);
+    the shapes of these tests are too small for the library to choose it by itself."""
+    from bnn_b200 import _lib as L
+    L.check(L.lib().bbb_debug_wgrad_split(request.param), 'bbb_debug_wgrad_split')
+    yield request.param
+    L.check(L.lib().bbb_debug_wgrad_split(0), 'bbb_debug_wgrad_split')
+
+
+@pytest.mark.parametrize('name', DEEP_BIG)
+def test_large_batch_fixture_with_wgrad_split(name, wgrad_split):
+    # the reference-generated 5-layer fixture (batch 640, S = 3) through the large-batch kernels, both wgrad schedules
+    PC.check_train_step(Case(name), DEV, fused=True, rtol=1e-5, rtol_gemm=RTOL_TF32, tf32=True)
+
+
+@pytest.mark.parametrize('B,d_in,hidden,S', [(400, 64, 96, 3), (1024, 128, 160, 2), (600, 36, 200, 1), (512, 96, 288, 5)])
+def test_batch_resident_train_step_matches_fp32_path(B, d_in, hidden, S, wgrad_split):
     """Forward (log-probs counted once per weight tile), dgrad (W^T sampled along i, (x > 0) mask in the drain) and
     the wgrad epilogue regenerate the same Philox eps: TF32 path == exact fp32 path within the TF32 bound."""
     mp = dict(input_shape=d_in, classes=10, batch_size=B, hidden_units=hidden, mode='classification',

@@ -88,3 +88,9 @@ for name, fn in (('forward', fwd), ('fwd post', lambda: fwd(L.F_SAMPLE | L.F_LOG
                  ('wgrad', lambda: bwd(L.F_NO_DX)), ('wgr post', lambda: bwd(L.F_NO_DX, relu=0))):
     us = timeit(fn)
     print(f'{name:8s} [{inn}x{out}] B={B} S={S}: {us:8.1f} us = {us / S:7.1f} us/sample, {flops / us / 1e6:6.1f} TFLOP/s', flush=True)
+if S >= 4:   # the sample-group split of wgrad (two CTAs per tile, partial gradients + combine kernel): off / by shape
+    for mode, name in ((-1, 'wgr 1cta'), (0, 'wgr auto')):
+        L.check(L.lib().bbb_debug_wgrad_split(mode), 'split')
+        us = timeit(lambda: bwd(L.F_NO_DX, relu=0))
+        print(f'{name:8s} [{inn}x{out}] B={B} S={S}: {us:8.1f} us = {us / S:7.1f} us/sample, {flops / us / 1e6:6.1f} TFLOP/s', flush=True)
+    L.check(L.lib().bbb_debug_wgrad_split(0), 'split')
