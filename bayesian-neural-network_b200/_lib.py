@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get('BBB_LIB') or os.path.join(_HERE, 'libbbb.so')   # BBB
 
 # flags (include/bbb.h)
 F_SAMPLE, F_LOGPROB, F_RELU_IN, F_ACCUM, F_TF32, F_NO_DX, F_SCALE_DX, F_NO_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128
-F_OUT_ZEROED, F_DX_PREACT, F_RELU_OUT = 256, 512, 1024
+F_OUT_ZEROED, F_DX_PREACT, F_RELU_OUT, F_ADAM_OVERLAP = 256, 512, 1024, 2048
 PRIOR_GAUSSIAN, PRIOR_MIXTURE = 0, 1
 NLL_NONE, NLL_CE, NLL_GAUSS = 0, 1, 2
 

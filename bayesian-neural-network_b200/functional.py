@@ -555,17 +555,21 @@ class _FusedELBO(torch.autograd.Function):
             # (parameters change here, no .grad appears); only the head's gradients are materialised (scratch)
             with torch.no_grad():
                 B = x2.shape[0]
-                hg = _alloc_grads(params[-1:])
-                tab = _mlp_layer_table(params, eps, ys, list(ctx.dxs[1:nl]) + [d_out], [None] * (nl - 1) + [hg[0]],
-                                       ctx.dxs[nl])
+                overlap = bool(getattr(ctx.fused_opt, 'overlap_backward', False))
+                if overlap:     # ordinary backward kernels + per-layer Adam on a side stream: every layer writes gradients
+                    sg = _alloc_grads(params)
+                else:           # update in the write-back: only the head writes its gradients
+                    sg = [None] * (nl - 1) + [_alloc_grads(params[-1:])[0]]
+                tab = _mlp_layer_table(params, eps, ys, list(ctx.dxs[1:nl]) + [d_out], sg, ctx.dxs[nl])
                 adam = (L.AdamFuse * nl)()
                 for l in range(nl):
                     d = ctx.fused_opt.fuse_descriptor(ctx.live[l])
                     C.memmove(C.byref(adam[l]), C.byref(d), C.sizeof(L.AdamFuse))
                 rng = eps.rng(0)
                 L.check(L.lib().bbb_mlp_bwd(tab, nl, L.ptr(x2), S, B, C.byref(rng), C.byref(prior),
-                                            L.F_SAMPLE | L.F_TF32, -beta / S, beta / S, L.ptr(bd), L.ptr(bd), 0,
-                                            L.ptr(scale), adam, L.stream()), 'bbb_mlp_bwd')
+                                            L.F_SAMPLE | L.F_TF32 | (L.F_ADAM_OVERLAP if overlap else 0), -beta / S,
+                                            beta / S, L.ptr(bd), L.ptr(bd), 0, L.ptr(scale), adam, L.stream()),
+                        'bbb_mlp_bwd')
             return (None,) * (9 + 4 * nl)
         if ctx.fused_opt is not None:     # Adam rides in the backward kernels: parameters change here, no .grad appears
             with torch.no_grad():

@@ -36,8 +36,12 @@ class GraphedTrainStep:
         # trip, no optimiser launch).  Off by default: measured on B200 at the MNIST-shape config the update then runs
         # as a memory-bound tail of every backward CTA and the step is slower (0.214 ms) than with the stand-alone
         # multi-tensor kernel at 92 % of HBM peak (0.188 ms).  With several GPUs the gradients are all-reduced first.
+        # fuse_optimizer='overlap': the ordinary backward kernels, each layer's Adam update on a side stream under the
+        # backward of the layer below (a parallel branch of the captured graph)
         self.optimizer_fused = bool(fuse_optimizer and world_size == 1 and hasattr(net, 'fuse_optimizer')
-                                    and x.shape[0] <= 128 and net.fuse_optimizer(optimizer))
+                                    and x.shape[0] <= 128
+                                    and net.fuse_optimizer(optimizer, overlap=(fuse_optimizer == 'overlap')))
+        self.optimizer_overlapped = self.optimizer_fused and fuse_optimizer == 'overlap' 
         # warm-up and capture must not train the model: snapshot parameters and optimiser state, restore after
         params = [p for g in optimizer.param_groups for p in g['params']]
         p_snap = [p.detach().clone() for p in params]

@@ -56,14 +56,18 @@ class BayesianNetwork(nn.Module):
     def layers(self):
         return [getattr(self, f'l{i + 1}') for i in range(self.n_layers)]
 
-    def fuse_optimizer(self, optimizer):
-        """Opt-in (single GPU): let the backward kernels of sample_elbo apply `optimizer`'s (bnn_b200.FusedAdam) next
-        step in their gradient epilogue -- loss.backward() then UPDATES the parameters and leaves .grad unset, and
-        the optimizer.step() that follows only advances the step count.  Returns False (and changes nothing) when
-        this network cannot run the fused tcgen05 backward.  fuse_optimizer(None) switches back."""
+    def fuse_optimizer(self, optimizer, overlap=False):
+        """Opt-in (single GPU): let the backward of sample_elbo apply `optimizer`'s (bnn_b200.FusedAdam) next step --
+        loss.backward() then UPDATES the parameters and leaves .grad unset, and the optimizer.step() that follows only
+        advances the step count.  overlap=False: the update rides in the backward kernels' gradient epilogue (measured
+        slower); overlap=True: the ordinary backward kernels run and every layer's Adam update is launched
+        on a side stream as soon as that layer's backward has finished, under the backward of the layer below
+        (BBB_F_ADAM_OVERLAP; network-level path only).  Returns False (and changes nothing) when this network cannot
+        run the fused tcgen05 backward.  fuse_optimizer(None) switches back."""
         if optimizer is None:
             self._fused_opt = None
             return True
+        optimizer.overlap_backward = bool(overlap)
         ok = (self.tf32 and self.fused and not self.local_reparam and self.batch_size <= 128 and
               all(l.weight_mu.shape[1] % 4 == 0 for l in self.layers()) and hasattr(optimizer, 'fuse_descriptor'))
         self._fused_opt = optimizer if ok else None

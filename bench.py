@@ -52,7 +52,7 @@ def parse():
     ap.add_argument('--eager', action='store_true', help='time the eager call sequence instead of the captured graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--fuse-opt', type=int, default=0,
-                    help='1: apply Adam inside the backward kernels (bbb_mlp_bwd with an Adam descriptor; measured slower on B200, see DESIGN.md); 0: one multi-tensor launch')
+                    help='0: Adam as one multi-tensor launch after the backward; 1: Adam inside the backward kernels\' write-back (measured slower on B200, DESIGN.md 4.6); 2: one Adam launch per layer on a side stream, overlapping the backward of the layer below')
     ap.add_argument('--no-extras', action='store_true', help='skip the fp32_exact / wide / unchanged-caller sub-records')
     ap.add_argument('--comm', default='peer', choices=['peer', 'nccl'],
                     help='N > 1: peer = gradient reduce-scatter + Adam + parameter all-gather in one kernel over NVLink '
@@ -585,7 +585,7 @@ def run_b200(args):
     if not args.eager:
         try:
             graphed = bnn_b200.GraphedTrainStep(net, opt, x_d, y_d, S, sigma=sigma, beta=beta, world_size=world,
-                                                fuse_optimizer=bool(args.fuse_opt) and world == 1)
+                                                fuse_optimizer=({1: True, 2: 'overlap'}.get(args.fuse_opt, False) if world == 1 else False))
             graph_note = 'whole step captured in one CUDA graph (bnn_b200.GraphedTrainStep), one replay per step'
         except Exception as e:          # e.g. a collective that cannot be captured: fall back to the eager sequence
             graphed, graph_note = None, f'eager call sequence (graph capture failed: {type(e).__name__}: {e})'
@@ -841,7 +841,9 @@ def run_b200(args):
                 higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='tf32' if tf32 else 'f32', data='synthetic',
                 config=dict(workload=workload_name(args.workload, w, S),
-                            optimizer=('Adam applied in the backward kernels\' gradient epilogue (bbb_linear_bwd_adam; same update rule as torch.optim.Adam)'
+                            optimizer=('Adam, one launch per layer on a side stream as soon as that layer\'s backward kernel has finished, overlapping the backward of the layer below (BBB_F_ADAM_OVERLAP; same update rule as torch.optim.Adam)'
+                                       if getattr(graphed, 'optimizer_overlapped', False) else
+                                       'Adam applied in the backward kernels\' gradient epilogue (bbb_linear_bwd_adam; same update rule as torch.optim.Adam)'
                                        if getattr(graphed, 'optimizer_fused', False) else
                                        ('Adam sharded over the ranks inside the peer-memory exchange kernel (bnn_b200.PeerShardedAdam, same update rule as torch.optim.Adam)'
                                         if peer else

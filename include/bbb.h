@@ -59,6 +59,11 @@ extern "C" {
                                no kernel spends shared-memory bandwidth on a ReLU pass over TMA-landed tiles.  Implemented
                                by the large-batch tensor kernels only: ask bbb_linear_fwd_relu_out_supported first; a
                                call that sets it on any other path returns BBB_EUNSUPPORTED. */
+#define BBB_F_ADAM_OVERLAP 2048 /* bbb_mlp_bwd with Adam descriptors: do NOT fuse the update into the gradient write-back;
+                               run the ordinary backward kernels (gradient pointers required) and launch each layer's
+                               Adam update on a side stream as soon as that layer's backward kernel has finished, so the
+                               bandwidth-bound update of layer l overlaps the latency-bound backward of layer l - 1.  The
+                               side stream is forked from and joined back into `stream` (graph-capture safe). */
 #define BBB_F_OUT_ZEROED 256 /* y (forward) / dx (backward) is already zero-filled by the caller: kernels that
                                combine split-K partial sums with red.add skip their own memset              */
 

@@ -89,10 +89,12 @@ def test_graphed_step_equals_eager_steps(name, tf32):
     assert losses_g[0] != losses_g[1]                   # fresh eps every replay
 
 
-@pytest.mark.parametrize('network_level', [False, True])
-def test_fused_optimizer_matches_separate_adam_on_gpu(network_level):
+@pytest.mark.parametrize('network_level,overlap', [(False, False), (True, False), (True, True)],
+                         ids=['layerwise', 'network', 'network-overlap'])
+def test_fused_optimizer_matches_separate_adam_on_gpu(network_level, overlap):
     """Adam in the backward's gradient write-back (bbb_mlp_bwd with an Adam descriptor / bbb_linear_bwd_adam) == the
-    same backward kernels + bbb_adam_step, same Philox draws.
+    same backward kernels + bbb_adam_step, same Philox draws.  overlap: the ordinary kernels with each layer's Adam
+    launched on a side stream under the backward of the layer below (BBB_F_ADAM_OVERLAP).
     One step, so the comparison is not blurred by the TF32 path's run-to-run reorder noise feeding Adam's sign."""
     from bnn_b200 import functional as F
     c = Case('cfg2_mnist_mix')
@@ -104,7 +106,7 @@ def test_fused_optimizer_matches_separate_adam_on_gpu(network_level):
         net = PC.build_net(c, DEV, tf32=True).train()
         opt = bnn_b200.FusedAdam(net.parameters(), lr=1e-3)
         if fuse:
-            assert net.fuse_optimizer(opt)
+            assert net.fuse_optimizer(opt, overlap=overlap)
         bnn_b200.manual_seed(77, 5)
         net.zero_grad()
         net.sample_elbo(x, y, c.beta, c.S)[0].backward()

@@ -242,8 +242,8 @@ def test_beta_may_be_a_tensor(fake):
     assert outs[0][0] == outs[1][0] and torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-9)
 
 
-@pytest.mark.parametrize('network_level', [True, False])
-def test_fused_optimizer_step_equals_backward_then_adam(fake, network_level, monkeypatch):
+@pytest.mark.parametrize('network_level,overlap', [(True, False), (True, True), (False, False)])
+def test_fused_optimizer_step_equals_backward_then_adam(fake, network_level, overlap, monkeypatch):
     """net.fuse_optimizer(opt): backward applies Adam inside bbb_mlp_bwd (network-level call) / bbb_linear_bwd_adam
     (per-layer calls) and leaves .grad unset; the parameters after 2 steps equal backward + FusedAdam.step()."""
     from bnn_b200 import functional as F
@@ -254,7 +254,7 @@ def test_fused_optimizer_step_equals_backward_then_adam(fake, network_level, mon
         net = PC.build_net(c, 'cpu', tf32=True).train()
         opt = bnn_b200.FusedAdam(net.parameters(), lr=1e-2)
         if fuse:
-            assert net.fuse_optimizer(opt)
+            assert net.fuse_optimizer(opt, overlap=overlap)
         with bnn_b200.eps_mode('reference'):
             torch.manual_seed(5)
             for _ in range(2):
