@@ -345,7 +345,9 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         }
       }
     }
-    if (st == 0) tma::bulk_wait_all();      // the partial tile has been added to the output (and its staging read)
+    // the staging tile must outlive the reduce-add's READ of it; the adds themselves complete with the grid (the next
+    // kernel's griddepcontrol.wait orders after that), so nobody waits for the L2 round trips here
+    if (st == 0) tma::bulk_wait_read();
   }
   stamp(tl, 15);
   tc_fence_before_sync();

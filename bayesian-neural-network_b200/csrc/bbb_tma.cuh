@@ -102,6 +102,9 @@ __device__ __forceinline__ void reduce_add_3d(const CUtensorMap *m, uint32_t sme
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// until the committed bulk operations have READ their shared-memory source (which may then be reused or released); their
+// global writes complete by the end of the grid at the latest, which is what a dependent grid waits for
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 }  // namespace tma
 }  // namespace bbb

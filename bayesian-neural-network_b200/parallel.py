@@ -128,3 +128,45 @@ def shard_samples(total_samples, rank, world_size):
     count = per + (1 if rank < rem else 0)
     first = rank * per + min(rank, rem)
     return first, count
+
+
+# ---- the minibatch-row axis ---------------------------------------------------------------------------------------------
+# north_star: "Monte-Carlo ELBO samples AND minibatch shards are partitioned across the GPUs".  Ranks that share a sample
+# block (same Philox sample indices -> the same sampled weights) split the ROWS of the minibatch.  With
+#     L = 1/S sum_s [ beta (log q_s - log p_s) + NLL_s(all rows) ]                                   (networks.py:199-209)
+# a rank holding the rows of shard j (of R) computes  l = sample_elbo(x_j, y_j, beta / R, S_local).loss : the rank-SUM of
+# l over the R row shards of a sample block is that block's loss, so the MEAN over all ranks of  R * l  is L -- and the mean
+# gradient every exchange here computes (all-reduce / R, PeerShardedAdam) is exactly dL.  No kernel knows about it.
+class ShardPlan:
+    """Where `rank` sits in the (sample blocks) x (row shards) grid of `world` ranks.
+    sample_first, sample_count: its block of global MC-sample indices (rng.set_sample_base(sample_first));
+    row_lo, row_hi: its rows of the minibatch;  row_shards: R;  beta_scale = 1 / R;  loss_scale = R."""
+
+    def __init__(self, rank, world, samples_total, batch, row_shards=None):
+        if row_shards is None:         # rows are only split when there are more ranks than samples
+            row_shards = 1
+            while world // row_shards > samples_total and world % (row_shards * 2) == 0:
+                row_shards *= 2
+        if world % row_shards != 0:
+            raise ValueError('row_shards must divide the world size')
+        self.rank, self.world, self.row_shards = rank, world, row_shards
+        self.sample_blocks = world // row_shards
+        self.block, self.row_index = rank // row_shards, rank % row_shards
+        self.sample_first, self.sample_count = shard_samples(samples_total, self.block, self.sample_blocks)
+        self.row_lo = self.row_index * batch // row_shards
+        self.row_hi = (self.row_index + 1) * batch // row_shards
+        self.beta_scale, self.loss_scale = 1.0 / row_shards, float(row_shards)
+
+    def rows(self, *tensors):
+        out = tuple(t[self.row_lo:self.row_hi] for t in tensors)
+        return out if len(out) > 1 else out[0]
+
+
+def sharded_elbo(net, x_rows, y_rows, beta, plan, sigma=1.0):
+    """sample_elbo of this rank's shard (x_rows, y_rows = plan.rows(x, y)).  Returns the 4-tuple of sample_elbo with the
+    loss already multiplied by plan.loss_scale: call .backward() on it and exchange gradients as usual (rank mean).  The
+    caller has set rng.set_sample_base(plan.sample_first).  Reporting: the rank mean of the returned loss is the full
+    loss; log prior / posterior are per sample block, the NLL is this shard's."""
+    fn = net.sample_elbo_lr if getattr(net, 'local_reparam', False) else net.sample_elbo
+    info = fn(x_rows, y_rows, beta * plan.beta_scale, plan.sample_count, sigma)
+    return (info[0] * plan.loss_scale,) + tuple(info[1:])

@@ -131,6 +131,35 @@ def test_fused_optimizer_matches_separate_adam_on_gpu(network_level, overlap):
         assert got <= max(0.1, 5 * floor + 0.02), (got, floor)     # (up to the TF32 path's reorder noise)
 
 
+@pytest.mark.parametrize('tf32', [False, True])
+def test_row_sharded_step_equals_full_batch(tf32):
+    """The minibatch-row axis (parallel.ShardPlan / sharded_elbo) on the real kernels: two row shards computed one after
+    the other with the same Philox stream, gradients averaged = the full-batch step's gradients."""
+    from bnn_b200 import parallel
+    c = Case('cfg2_mnist_mix')
+    x, y = c.x.to(DEV), c.y.to(DEV)
+    net = PC.build_net(c, DEV, tf32=tf32).train()
+    bnn_b200.manual_seed(11, 3)
+    net.zero_grad()
+    full = net.sample_elbo(x, y, c.beta, c.S)
+    full[0].backward()
+    want = [p.grad.clone() for p in net.parameters()]
+    acc, loss = [torch.zeros_like(p) for p in net.parameters()], 0.0
+    for r in range(2):
+        plan = parallel.ShardPlan(r, 2, c.S, x.shape[0], row_shards=2)
+        bnn_b200.manual_seed(11, 3)
+        net.zero_grad()
+        info = parallel.sharded_elbo(net, *plan.rows(x, y), c.beta, plan)
+        info[0].backward()
+        loss += float(info[0].detach()) / 2
+        for a, p in zip(acc, net.parameters()):
+            a += p.grad / 2
+    rtol = 5e-3 if tf32 else 2e-5
+    assert abs(loss - float(full[0].detach())) <= rtol * abs(float(full[0].detach()))
+    for a, b in zip(acc, want):
+        assert float((a - b).abs().max()) <= rtol * float(b.abs().max())
+
+
 def test_peer_adam_kernel_two_ranks_on_one_device():
     """bbb_adam_step_peer with two 'ranks' whose buffers live on this one GPU, launched on two streams: the flag
     barriers in (peer) memory let them meet, each reduces its slice of BOTH gradient buckets, updates with its own

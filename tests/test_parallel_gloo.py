@@ -86,6 +86,61 @@ def test_two_rank_sample_sharding_matches_single_process(monkeypatch, overlap):
     np.testing.assert_allclose(got['scal'].numpy(), [float(v.detach()) for v in info], rtol=2e-6)
 
 
+def _row_worker(rank, world, port, out_path):
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        fake_bbb.install(_Patch())
+        case = Case(CASE)
+        plan = parallel.ShardPlan(rank, world, S_TOTAL, case.x.shape[0], row_shards=world)   # every rank: all samples
+        assert (plan.sample_first, plan.sample_count) == (0, S_TOTAL)
+        net = PC.build_net(case, 'cpu')
+        net.train()
+        eps = _all_eps(case)
+        bnn_b200.rng.set_injected_eps([t for per in eps for pair in per for t in pair])
+        with bnn_b200.eps_mode('injected'):
+            info = parallel.sharded_elbo(net, *plan.rows(case.x, case.y), case.beta, plan, sigma=case.sigma)
+        info[0].backward()
+        parallel.allreduce_gradients(net, world)
+        loss = parallel.allreduce_scalars(info[:1], world)
+        if rank == 0:
+            torch.save(dict(grads=PC.net_grads(net), loss=loss), out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_row_sharding_matches_single_process(monkeypatch):
+    """The minibatch-row axis: both ranks run ALL samples (same eps) on half of the rows with beta / 2 and the loss
+    doubled; the rank-mean gradients and loss equal the one-process full-batch step."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    out_path = os.path.join(tempfile.mkdtemp(), 'rank0.pt')
+    mp.spawn(_row_worker, args=(2, port, out_path), nprocs=2, join=True)
+    got = torch.load(out_path, weights_only=False)
+    fake_bbb.install(monkeypatch)
+    case = Case(CASE)
+    net, info = _run(case, _all_eps(case), S_TOTAL)
+    for a, b in zip(got['grads'], PC.net_grads(net)):
+        for ga, gb in zip(a, b):
+            assert np.abs(ga - gb).max() <= 2e-6 * np.abs(gb).max()
+    np.testing.assert_allclose(got['loss'].numpy(), [float(info[0].detach())], rtol=2e-6)
+
+
+def test_shard_plan_grid():
+    # more ranks than samples: the surplus factor goes to the rows; every (sample, row) pair is covered exactly once
+    for world, S, B in ((8, 2, 128), (8, 64, 4096), (4, 1, 64), (2, 2, 128), (8, 3, 100)):
+        plans = [parallel.ShardPlan(r, world, S, B) for r in range(world)]
+        assert all(p.row_shards * p.sample_blocks == world for p in plans)
+        assert plans[0].row_shards == (1 if S >= world else plans[0].row_shards) and (S >= world or plans[0].row_shards > 1)
+        seen = {}
+        for p in plans:
+            for s_ in range(p.sample_first, p.sample_first + p.sample_count):
+                for r_ in range(p.row_lo, p.row_hi):
+                    seen[(s_, r_)] = seen.get((s_, r_), 0) + 1
+        assert len(seen) == S * B and set(seen.values()) == {1}
+
+
 def test_shard_samples_partitions_exactly():
     for total in (1, 2, 5, 64):
         for world in (1, 2, 3, 8):
