@@ -66,7 +66,8 @@ def test_graphed_step_equals_eager_steps(name, tf32):
         return net_e, losses
 
     net_e, losses_e = eager_run()
-    np.testing.assert_allclose(losses_g, losses_e, rtol=1e-5 if not tf32 else 1e-4)
+    # (TF32: the third loss already sees two Adam steps whose sign-flipped weights differ between any two runs)
+    np.testing.assert_allclose(losses_g, losses_e, rtol=1e-5 if not tf32 else 5e-4)
     if not tf32:
         for p, q in zip(net_g.parameters(), net_e.parameters()):
             assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), float((p - q).abs().max())
@@ -84,7 +85,9 @@ def test_graphed_step_equals_eager_steps(name, tf32):
         for p, q, q2 in zip(net_g.parameters(), net_e.parameters(), net_e2.parameters()):
             floor = mismatch(q, q2)
             got = mismatch(p, q)
-            assert got <= max(0.03, 3 * floor + 0.01), (got, floor)
+            # the floor itself moves from run to run (one failure in ~10 full-suite runs at 3 * floor + 0.01): the count
+            # bound is loose, the size bound below is exact (3 steps of at most 2 lr)
+            assert got <= max(0.05, 5 * floor + 0.02), (got, floor)
             assert float((p - q).abs().max()) <= 3 * 2 * 1e-3 * 1.05
     assert losses_g[0] != losses_g[1]                   # fresh eps every replay
 
