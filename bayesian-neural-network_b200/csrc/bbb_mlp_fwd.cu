@@ -345,9 +345,9 @@ ws_fwd_kernel(const __grid_constant__ CUtensorMap tm_mu, const __grid_constant__
         }
       }
     }
-    // the staging tile must outlive the reduce-add's READ of it; the adds themselves complete with the grid (the next
-    // kernel's griddepcontrol.wait orders after that), so nobody waits for the L2 round trips here
-    if (st == 0) tma::bulk_wait_read();
+    // the partial tile has been added to the output (and its staging read).  Waiting only for the READ of the staging
+    // tile (cp.async.bulk.wait_group.read) was measured: no gain -- the grid's completion waits for the adds anyway
+    if (st == 0) tma::bulk_wait_all();
   }
   stamp(tl, 15);
   tc_fence_before_sync();
