@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(WT, 1) wide_kernel(const __grid_constant__ CUt
   const bool lpcta = kLogProb && (int)blockIdx.y < CL;
   // sampler groups: with CL = 4 a CTA's piece of a stage is 256 quads, so the 512 sampler threads split into two
   // groups that take alternate k blocks
-  constexpr int G = CL == 4 ? 2 : 1, T = STH / G, QPT = (1024 / CL) / T, PIECE = WBYTES / CL;
+  constexpr int G = CL >= 4 ? CL / 2 : 1, T = STH / G, QP = 1024 / CL, QPT = QP / T, PIECE = WBYTES / CL;
 
   // ---- setup ----------------------------------------------------------------------------------------
   if (warp == SW) tmem_alloc(smem_u32(&ctl.tmem_base), 512);
@@ -190,19 +190,19 @@ __global__ void __launch_bounds__(WT, 1) wide_kernel(const __grid_constant__ CUt
       if (kb >= WS) mbar_wait(smem_u32(&ctl.w_empty[wst]), (uint32_t)(((kb / WS) - 1) & 1));
 #pragma unroll
       for (int j = 0; j < QPT; ++j) {
-        const int q = t + j * T;                 // quad of this CTA's piece
+        const int gq = (int)rank * QP + t + j * T;       // quad of the tile; this CTA's piece is the range [rank QP, +QP)
         float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t off;
         int64_t o, i;
         if (!kDgrad) {
-          // piece = rows [128 / CL * rank, +128 / CL) of the [128 o][32 k] tile
-          const int row = (int)rank * (BM / CL) + (q >> 3), chunk = q & 7;
+          // [128 o][32 k] K-major: 8 quads per row, so the piece is 128 / CL consecutive rows
+          const int row = gq >> 3, chunk = gq & 7;
           o = m0 + row; i = (int64_t)kb * BK + chunk * 4;
           off = sw128_off(row, chunk);
         } else {
-          // piece = regions [4 / CL * rank, +4 / CL) of the 4 [32 o rows][32 i] regions (W^T as an MN-major operand:
-          // a quad of 4 consecutive i of one weight row o is ONE 16-byte store, nothing is transposed)
-          const int region = (int)rank * (4 / CL) + (q >> 8), kr = (q & 255) >> 3, c16 = q & 7;
+          // W^T as an MN-major operand: 4 regions of [32 o rows][32 i], 256 quads each; a quad of 4 consecutive i of one
+          // weight row o is ONE 16-byte store, nothing is transposed.  The piece is 4 / CL regions (or half of one)
+          const int region = gq >> 8, kr = (gq & 255) >> 3, c16 = gq & 7;
           o = (int64_t)kb * BK + kr; i = m0 + 32 * region + 4 * c16;
           off = (uint32_t)region * 4096u + mn32_off(kr, c16);
         }
@@ -358,6 +358,8 @@ int launch_wide(const LinArgs &a, cudaStream_t st) {
   const int n_bt = cdiv_w(a.B, NBT);
   dim3 grid(cdiv_w(kDgrad ? a.in : a.out, BM), n_bt, (unsigned)a.S);
   static const int max_cl = [] { const char *e = getenv("BBB_WIDE_CL"); return e ? atoi(e) : 4; }();   // (experiments)
+  // (clusters of 8 -- 15 co-resident on a B200 -- were tried for the energy they would save and did not complete: not
+  // instantiated)
   if (n_bt % 4 == 0 && max_cl >= 4) return launch_wide_cl<kDgrad, kLogProb, 4>(tm, a, grid, st);
   if (n_bt % 2 == 0 && max_cl >= 2) return launch_wide_cl<kDgrad, kLogProb, 2>(tm, a, grid, st);
   return launch_wide_cl<kDgrad, kLogProb, 1>(tm, a, grid, st);
