@@ -32,6 +32,15 @@ class GraphedTrainStep:
         self._ar = parallel.OverlappedAllReduce(1 if getattr(optimizer, 'reduces_gradients', False) else world_size)
         if hasattr(optimizer, 'use_device_step'):
             optimizer.use_device_step(self.counter)
+        # Learning-rate schedulers (reg_task.py:53-54 / class_task.py:60-61: StepLR) change param_groups[...]['lr'] on the
+        # host; the captured Adam launch has the initial lr baked in and multiplies it by this device scalar, which
+        # __call__ refreshes whenever the host value has moved (one tiny fill, only on the steps where it changes)
+        self._lr0 = float(optimizer.param_groups[0]['lr'])
+        self._lr_seen = self._lr0
+        self.lr_scale = None
+        if hasattr(optimizer, 'lr_scale_dev') and self._lr0 > 0:
+            self.lr_scale = torch.ones(1, dtype=torch.float32, device=dev)
+            optimizer.lr_scale_dev = self.lr_scale
         # Opt-in, one GPU: the optimiser's update rides in the backward kernels' gradient epilogue (no gradient round
         # trip, no optimiser launch).  Off by default: measured on B200 at the MNIST-shape config the update then runs
         # as a memory-bound tail of every backward CTA and the step is slower (0.214 ms) than with the stand-alone
@@ -95,5 +104,10 @@ class GraphedTrainStep:
             self.y.copy_(y, non_blocking=True)
         if beta is not None:
             self.beta.fill_(float(beta))
+        if self.lr_scale is not None:
+            lr = float(self.opt.param_groups[0]['lr'])
+            if lr != self._lr_seen:            # a scheduler stepped: every group moves by the same factor (StepLR)
+                self._lr_seen = lr
+                self.lr_scale.fill_(lr / self._lr0)
         self.graph.replay()
         return self.loss_info

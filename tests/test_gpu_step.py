@@ -134,6 +134,36 @@ def test_fused_optimizer_matches_separate_adam_on_gpu(network_level, overlap):
         assert got <= max(0.1, 5 * floor + 0.02), (got, floor)     # (up to the TF32 path's reorder noise)
 
 
+def test_graphed_step_follows_a_step_lr_scheduler():
+    """reg_task.py:53-54 / class_task.py:60-61 drive the optimiser with torch's StepLR.  The captured Adam launch has the
+    initial lr baked in; GraphedTrainStep scales it by a device scalar it refreshes when the host lr has moved.  Four
+    steps with the lr halved after every step: graph == eager (exact fp32 kernels)."""
+    c = Case('small_cls_mix')
+    x, y = c.x.to(DEV), c.y.to(DEV)
+    out = []
+    for graphed in (False, True):
+        net = PC.build_net(c, DEV, tf32=False).train()
+        opt = bnn_b200.FusedAdam(net.parameters(), lr=1e-2)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)
+        if graphed:
+            bnn_b200.manual_seed(9, 50)
+            gs = bnn_b200.GraphedTrainStep(net, opt, x, y, c.S, sigma=c.sigma, beta=c.beta, warmup=2)
+        else:
+            bnn_b200.manual_seed(9, 52)       # the capture consumed warmup + 1 host steps and baked step 52
+        for k in range(4):
+            if graphed:
+                gs(x, y)
+            else:
+                net.zero_grad()
+                net.sample_elbo(x, y, c.beta, c.S, sigma=c.sigma)[0].backward()
+                opt.step()
+            sched.step()
+        out.append([p.detach().clone() for p in net.parameters()])
+    assert opt.param_groups[0]['lr'] == pytest.approx(1e-2 / 16)
+    for p, q in zip(*out):
+        assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), float((p - q).abs().max())
+
+
 @pytest.mark.parametrize('tf32', [False, True])
 def test_row_sharded_step_equals_full_batch(tf32):
     """The minibatch-row axis (parallel.ShardPlan / sharded_elbo) on the real kernels: two row shards computed one after
