@@ -613,8 +613,11 @@ def run_b200(args):
             else:
                 fn(x_d, y_d)
             e1.record()
-            if e2e or world > 1:
-                e1.synchronize()                 # the caller reads the loss every step (N > 1: same per-step rendezvous)
+            if e2e:
+                e1.synchronize()                 # the caller reads the loss every step
+            # (`value` at N > 1: the rendezvous above is a device-side collective on the same stream, so the ranks'
+            #  timed regions start together without the host waiting in between -- as at N = 1, the host runs ahead
+            #  and no launch latency is exposed inside the brackets)
             evs.append((e0, e1))
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
