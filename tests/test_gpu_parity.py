@@ -281,6 +281,15 @@ def test_c_abi_rejects_bad_arguments():
     acc = torch.zeros(1, dtype=torch.float64, device=DEV)
     assert lib.bbb_kl_gauss(t.data_ptr(), t.data_ptr(), -1.0, 8, acc.data_ptr(), None) == -1
     assert lib.bbb_kl_gauss(t.data_ptr(), t.data_ptr(), 1.0, 0, acc.data_ptr(), None) == 0   # empty input is fine
+    # BBB_F_RELU_OUT is a large-batch tensor-path feature: asked of any other path it is refused, not ignored
+    L = bnn_b200._lib
+    assert lib.bbb_linear_fwd_relu_out_supported(128, 64, 64, L.F_TF32) == 0
+    assert lib.bbb_linear_fwd_relu_out_supported(512, 64, 64, L.F_TF32) == 1
+    assert lib.bbb_linear_fwd_relu_out_supported(512, 64, 64, 0) == 0
+    x, w, b, y = (torch.zeros(n, device=DEV) for n in (128 * 64, 64 * 64, 64, 128 * 64))
+    rc = lib.bbb_linear_fwd(x.data_ptr(), 0, w.data_ptr(), w.data_ptr(), b.data_ptr(), b.data_ptr(), None, None, None, None,
+                            1, 128, 64, 64, L.F_TF32 | L.F_RELU_OUT, y.data_ptr(), None, None, None)
+    assert rc == -3 and b'BBB_F_RELU_OUT' in lib.bbb_last_error_string()
 
 
 def test_empty_batch():
