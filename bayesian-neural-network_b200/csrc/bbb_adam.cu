@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "bbb_common.cuh"
+#include "bbb_mlp.h"
 
 namespace bbb {
 namespace {
@@ -121,8 +122,16 @@ struct PeerArgs {
   uint32_t step;
   const uint32_t *step_dev;
   const float *lr_scale_dev;
+  unsigned long long *tl;      // debug (bbb_debug_set_timeline): phase stamps of block 0 / the last block, or NULL
 };
 
+__device__ __forceinline__ void pstamp(unsigned long long *tl, int slot) {
+  if (tl) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[slot] = t;
+  }
+}
 __device__ __forceinline__ void st_flag_sys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -148,6 +157,8 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
   __shared__ AdamConst cs;
   __shared__ uint32_t last_s;
   const int W = a.world, tid = threadIdx.x;
+  unsigned long long *tl0 = (a.tl && blockIdx.x == 0 && tid == 0) ? a.tl : nullptr;
+  pstamp(tl0, 0);
   const uint32_t e = *reinterpret_cast<volatile uint32_t *>(a.epoch) + 1u;   // this call's number (same in every block)
   if (tid == 0) cs = adam_consts(a.lr, a.b1, a.b2, a.eps, a.step, a.step_dev, a.lr_scale_dev);
   // ---- entry barrier: block 0 announces this rank, every block waits for all ranks
@@ -159,12 +170,16 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
     wait_flag(a.flags[a.rank] + tid, e, a.done + 1);
   }
   __syncthreads();
+  pstamp(tl0, 1);                       // every rank's gradients are complete
   const AdamConst c = cs;
   const float inv_w = 1.0f / (float)W;
   // ---- this rank's slice, in 16-byte quads; the last rank also takes the n % 4 tail
   const int64_t nq = a.n >> 2;
   const int64_t q_lo = nq * a.rank / W, q_hi = nq * (a.rank + 1) / W;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // (Measured with tools/time_peer_adam.py at 2 GPUs: entry barrier 6 us, reads + update 19-25 us, drain of the peer
+  //  stores 12-14 us, exit barrier 4-6 us.  A two-deep software pipeline that overlaps the inbound reads with the outbound
+  //  writes took the same 36 us for the middle two: not kept.)
   for (int64_t q = q_lo + (int64_t)blockIdx.x * blockDim.x + tid; q < q_hi; q += stride) {
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -198,17 +213,22 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
     for (int k = 0; k < W; ++k) a.p[k][i] = P;
   }
   // ---- exit barrier: the last block to finish announces this rank and waits for the others
+  pstamp(tl0, 2);                       // block 0: loads, update and stores issued
   __threadfence_system();             // this thread's peer stores are performed
   __syncthreads();
+  pstamp(tl0, 3);                       // block 0: its peer stores are performed
   if (tid == 0) last_s = atomicAdd(a.done, 1u) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
   if (last_s) {
+    unsigned long long *tl1 = (a.tl && tid == 0) ? a.tl : nullptr;
+    pstamp(tl1, 4);                     // the last block of this rank has finished
     if (tid < W) {
       __threadfence_system();
       st_flag_sys(a.flags[tid] + W + a.rank, e);
       wait_flag(a.flags[a.rank] + W + tid, e, a.done + 1);
     }
     __syncthreads();
+    pstamp(tl1, 5);                     // every rank has finished
     if (tid == 0) { *a.done = 0u; *a.epoch = e; }
   }
 }
@@ -266,6 +286,7 @@ extern "C" int bbb_adam_step_peer(const bbb_peer_comm *comm, float *exp_avg, flo
   a.m = exp_avg; a.v = exp_avg_sq; a.n = n;
   a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = (float)eps; a.step = step; a.step_dev = step_dev;
   a.lr_scale_dev = lr_scale_dev;
+  a.tl = peer_timeline();
   // every block must be able to run while block 0 is still waiting at the entry barrier, and the grid of every rank
   // must make progress independently: at most 4 blocks per SM, so the grid is always co-resident
   const int64_t slice_q = (n >> 2) / comm->world + 1;

@@ -19,6 +19,7 @@ unsigned long long *g_timeline = nullptr;
 int g_timeline_launch = 0;
 }
 // (every launch gets its own 160 x 16 slice of the buffer, 8 slices, in launch order)
+unsigned long long *peer_timeline() { return g_timeline ? g_timeline + (size_t)8 * 2560 : nullptr; }
 unsigned long long *debug_timeline() { return g_timeline ? g_timeline + (size_t)(g_timeline_launch++ % 8) * 2560 : nullptr; }
 }  // namespace bbb
 

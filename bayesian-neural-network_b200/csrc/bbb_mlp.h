@@ -58,6 +58,8 @@ struct MlpBwdArgs {
 
 // debug: phase time stamps of the network-level kernels (tools/kernel_timeline.py)
 unsigned long long *debug_timeline();
+// the peer-exchange kernel's six stamps: slot 8 of the same buffer (words 20480..20485), or NULL
+unsigned long long *peer_timeline();
 __device__ __forceinline__ void stamp(unsigned long long *tl, int slot) {
   if (tl) {
     unsigned long long t;
