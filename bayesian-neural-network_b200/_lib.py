@@ -34,7 +34,8 @@ class AdamFuse(C.Structure):
 class PeerComm(C.Structure):
     """struct bbb_peer_comm: every rank's gradient bucket / parameter buffer / flag words as mapped in this process"""
     _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('grads', C.c_void_p * 8), ('params', C.c_void_p * 8),
-                ('flags', C.c_void_p * 8), ('epoch', C.c_void_p), ('done_blocks', C.c_void_p)]
+                ('flags', C.c_void_p * 8), ('epoch', C.c_void_p), ('done_blocks', C.c_void_p),
+                ('mc_grads', C.c_void_p), ('mc_params', C.c_void_p)]
 
 
 class MlpLayer(C.Structure):

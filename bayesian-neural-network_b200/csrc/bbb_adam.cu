@@ -123,7 +123,21 @@ struct PeerArgs {
   const uint32_t *step_dev;
   const float *lr_scale_dev;
   unsigned long long *tl;      // debug (bbb_debug_set_timeline): phase stamps of block 0 / the last block, or NULL
+  const float *mc_g;           // NVLS multicast mappings of the gradient / parameter buffers, or NULL
+  float *mc_p;
 };
+
+// sum over every rank's copy of 16 bytes, formed by the NVSwitch; store of 16 bytes to every rank's copy
+__device__ __forceinline__ float4 multimem_ld_sum4(const float *mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st4(float *mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 
 __device__ __forceinline__ void pstamp(unsigned long long *tl, int slot) {
   if (tl) {
@@ -180,13 +194,18 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
   // (Measured with tools/time_peer_adam.py at 2 GPUs: entry barrier 6 us, reads + update 19-25 us, drain of the peer
   //  stores 12-14 us, exit barrier 4-6 us.  A two-deep software pipeline that overlaps the inbound reads with the outbound
   //  writes took the same 36 us for the middle two: not kept.)
+  const bool nvls_ld = a.mc_g != nullptr, nvls_st = a.mc_p != nullptr;
   for (int64_t q = q_lo + (int64_t)blockIdx.x * blockDim.x + tid; q < q_hi; q += stride) {
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nvls_ld) {
+      G = multimem_ld_sum4(a.mc_g + 4 * q);
+    } else {
 #pragma unroll
-    for (int k = 0; k < BBB_MAX_PEERS; ++k) {
-      if (k < W) {
-        const float4 t = __ldcg(reinterpret_cast<const float4 *>(a.g[k]) + q);   // peer memory: never through L1
-        G.x += t.x; G.y += t.y; G.z += t.z; G.w += t.w;
+      for (int k = 0; k < BBB_MAX_PEERS; ++k) {
+        if (k < W) {
+          const float4 t = __ldcg(reinterpret_cast<const float4 *>(a.g[k]) + q);   // peer memory: never through L1
+          G.x += t.x; G.y += t.y; G.z += t.z; G.w += t.w;
+        }
       }
     }
     G.x *= inv_w; G.y *= inv_w; G.z *= inv_w; G.w *= inv_w;
@@ -198,9 +217,13 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerArgs a) {
     adam1(P.w, G.w, M.w, V.w, c);
     reinterpret_cast<float4 *>(a.m)[q] = M;
     reinterpret_cast<float4 *>(a.v)[q] = V;
+    if (nvls_st) {
+      multimem_st4(a.mc_p + 4 * q, P);
+    } else {
 #pragma unroll
-    for (int k = 0; k < BBB_MAX_PEERS; ++k)
-      if (k < W) reinterpret_cast<float4 *>(a.p[k])[q] = P;
+      for (int k = 0; k < BBB_MAX_PEERS; ++k)
+        if (k < W) reinterpret_cast<float4 *>(a.p[k])[q] = P;
+    }
   }
   if (a.rank == W - 1 && blockIdx.x == 0 && tid < (a.n & 3)) {
     const int64_t i = (nq << 2) + tid;
@@ -287,6 +310,8 @@ extern "C" int bbb_adam_step_peer(const bbb_peer_comm *comm, float *exp_avg, flo
   a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = (float)eps; a.step = step; a.step_dev = step_dev;
   a.lr_scale_dev = lr_scale_dev;
   a.tl = peer_timeline();
+  a.mc_g = comm->mc_grads; a.mc_p = comm->mc_params;
+  BBB_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.mc_g) | reinterpret_cast<uintptr_t>(a.mc_p)) & 15u) == 0, "multicast mappings must be 16-byte aligned");
   // every block must be able to run while block 0 is still waiting at the entry barrier, and the grid of every rank
   // must make progress independently: at most 4 blocks per SM, so the grid is always co-resident
   const int64_t slice_q = (n >> 2) / comm->world + 1;

@@ -3,6 +3,7 @@ kernel launch (csrc/bbb_adam.cu).  Opt-in: the reference's callers 
 torch.optim.Adam; GraphedTrainStep and bench.py use this one because the stock foreach implementation costs
 more than the whole fused forward+backward at the MNIST-shape config."""
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -156,8 +157,24 @@ class PeerShardedAdam(torch.optim.Optimizer):
         dev = params[0].device
         self.n = sum(p.numel() for p in params)
         npad = (self.n + 3) // 4 * 4
-        self.flat_p = torch.zeros(npad, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(npad, dtype=torch.float32, device=dev)
+        # NVLS: when torch's symmetric memory comes up on this node WITH a multicast mapping, the parameter buffer and the
+        # gradient bucket are allocated from it, and the kernel reads its slice of the gradient sum with multimem.ld_reduce
+        # (the NVSwitch adds the ranks' copies: inbound n/W instead of (W-1) n/W) and writes the new parameters with
+        # multimem.st.  Measured inside the captured MNIST-shape step (tools/time_peer_adam.py): 8 GPUs 190 us against
+        # 207 us with peer loads / stores (the in-switch reduction alone: 196 us); 4 GPUs 191 against 185 us; 2 GPUs 191
+        # against 165 us -- so it is used above 4 ranks.  BBB_PEER_NVLS=0: never, =force: at any world size.
+        self.mc_p = self.mc_g = 0
+        self._symm = None
+        mode = os.environ.get('BBB_PEER_NVLS', '1')
+        want = multi and self.world > 1 and mode != '0' and (self.world > 4 or mode in ('force', '2'))
+        symm = self._symmetric_buffers(npad, dev, group) if want else None
+        if symm is not None:
+            self.flat_p, self.flat_g, self._symm = symm[0], symm[1], symm[2:]
+            self.flat_p.zero_()
+            self.flat_g.zero_()
+        else:
+            self.flat_p = torch.zeros(npad, dtype=torch.float32, device=dev)
+            self.flat_g = torch.zeros(npad, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(npad, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(npad, dtype=torch.float32, device=dev)
         self.flags = torch.zeros(2 * 8, dtype=torch.int32, device=dev)
@@ -178,8 +195,15 @@ class PeerShardedAdam(torch.optim.Optimizer):
         F.grad_buckets[self.flat_p.data_ptr()] = (self.flat_g, weakref.ref(self))
         if self.world > 1:
             dist.broadcast(self.flat_p, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-            self.peer_p = open_peers(self.flat_p, group)
-            self.peer_g = open_peers(self.flat_g, group)
+            if self._symm is not None:
+                hp, hg = self._symm
+                self.peer_p, self.peer_g = [int(q) for q in hp.buffer_ptrs], [int(q) for q in hg.buffer_ptrs]
+                self.mc_p, self.mc_g = int(hp.multicast_ptr), int(hg.multicast_ptr)
+                if os.environ.get('BBB_PEER_NVLS', '1') == '2':      # (experiments) in-switch reduction only
+                    self.mc_p = 0
+            else:
+                self.peer_p = open_peers(self.flat_p, group)
+                self.peer_g = open_peers(self.flat_g, group)
             self.peer_f = open_peers(self.flags, group)
             dist.barrier(group)
         else:
@@ -191,6 +215,28 @@ class PeerShardedAdam(torch.optim.Optimizer):
 
     def use_device_step(self, counter):
         self.step_dev = counter
+
+    @staticmethod
+    def _symmetric_buffers(npad, dev, group):
+        """(flat_p, flat_g, handle_p, handle_g) from torch's symmetric memory when every rank gets a multicast mapping
+        for both, else None -- decided collectively, so that all ranks take the same path."""
+        import torch.distributed as dist
+        ok, out = 0, None
+        if True:
+            try:
+                import torch.distributed._symmetric_memory as sm
+                g = group if group is not None else dist.group.WORLD
+                fp = sm.empty(npad, dtype=torch.float32, device=dev)
+                fg = sm.empty(npad, dtype=torch.float32, device=dev)
+                hp, hg = sm.rendezvous(fp, g), sm.rendezvous(fg, g)
+                if (int(hp.multicast_ptr) and int(hg.multicast_ptr) and int(hp.buffer_ptrs[hp.rank]) == fp.data_ptr()
+                        and int(hg.buffer_ptrs[hg.rank]) == fg.data_ptr()):
+                    ok, out = 1, (fp, fg, hp, hg)
+            except Exception:
+                ok, out = 0, None
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return out if int(flag) == 1 else None
 
     def zero_grad(self, set_to_none=True):
         """Always drops the gradients: a p.grad kept alive would alias the shared bucket (functional._bucket_for)."""
@@ -219,6 +265,7 @@ class PeerShardedAdam(torch.optim.Optimizer):
         for k in range(self.world):
             c.grads[k], c.params[k], c.flags[k] = self.peer_g[k], self.peer_p[k], self.peer_f[k]
         c.epoch, c.done_blocks = self.words[0:1].data_ptr(), self.words[1:2].data_ptr()
+        c.mc_grads, c.mc_params = (self.mc_g or None), (self.mc_p or None)
         return c
 
     @torch.no_grad()

@@ -312,6 +312,12 @@ typedef struct bbb_peer_comm {
   uint32_t *flags[BBB_MAX_PEERS];
   uint32_t *epoch;
   uint32_t *done_blocks;
+  const float *mc_grads;   /* optional NVLS multicast mappings of the SAME gradient / parameter buffers (every rank's copy  */
+  float *mc_params;        /* bound to one multicast object, e.g. torch symmetric memory's multicast_ptr).  With mc_grads
+                              the kernel reads its slice of the gradient SUM with one multimem.ld_reduce per 16 bytes
+                              (the NVSwitch adds the W copies: inbound traffic n/W instead of (W-1) n/W); with mc_params it
+                              writes the new parameters to every rank with one multimem.st (outbound n/W likewise).
+                              NULL: peer loads / stores through grads[] / params[] */
 } bbb_peer_comm;
 /* let kernels of the CURRENT device load / store memory of `peer_device` (cudaDeviceEnablePeerAccess; idempotent) */
 int bbb_enable_peer_access(int32_t peer_device);
