@@ -166,7 +166,9 @@ class PeerShardedAdam(torch.optim.Optimizer):
         self.mc_p = self.mc_g = 0
         self._symm = None
         mode = os.environ.get('BBB_PEER_NVLS', '1')
-        want = multi and self.world > 1 and mode != '0' and (self.world > 4 or mode in ('force', '2'))
+        # (buffers above 64 MB -- config 5's 537 MB -- keep the peer path: the exchange is a per-cent of that step, and
+        #  multicast mappings of that size were not exercised)
+        want = (multi and self.world > 1 and mode != '0' and (mode in ('force', '2') or (self.world > 4 and npad * 4 <= (64 << 20))))
         symm = self._symmetric_buffers(npad, dev, group) if want else None
         if symm is not None:
             self.flat_p, self.flat_g, self._symm = symm[0], symm[1], symm[2:]
@@ -221,22 +223,29 @@ class PeerShardedAdam(torch.optim.Optimizer):
         """(flat_p, flat_g, handle_p, handle_g) from torch's symmetric memory when every rank gets a multicast mapping
         for both, else None -- decided collectively, so that all ranks take the same path."""
         import torch.distributed as dist
-        ok, out = 0, None
-        if True:
-            try:
-                import torch.distributed._symmetric_memory as sm
-                g = group if group is not None else dist.group.WORLD
-                fp = sm.empty(npad, dtype=torch.float32, device=dev)
-                fg = sm.empty(npad, dtype=torch.float32, device=dev)
-                hp, hg = sm.rendezvous(fp, g), sm.rendezvous(fg, g)
-                if (int(hp.multicast_ptr) and int(hg.multicast_ptr) and int(hp.buffer_ptrs[hp.rank]) == fp.data_ptr()
-                        and int(hg.buffer_ptrs[hg.rank]) == fg.data_ptr()):
-                    ok, out = 1, (fp, fg, hp, hg)
-            except Exception:
-                ok, out = 0, None
-        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        return out if int(flag) == 1 else None
+        def agree(ok):
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return int(flag) == 1
+        sm = fp = fg = None
+        try:
+            import torch.distributed._symmetric_memory as sm
+            fp = sm.empty(npad, dtype=torch.float32, device=dev)
+            fg = sm.empty(npad, dtype=torch.float32, device=dev)
+        except Exception:
+            fp = fg = None
+        if not agree(fp is not None and fg is not None):      # (nobody enters the rendezvous unless everybody allocated)
+            return None
+        out = None
+        try:
+            g = group if group is not None else dist.group.WORLD
+            hp, hg = sm.rendezvous(fp, g), sm.rendezvous(fg, g)
+            if (int(hp.multicast_ptr) and int(hg.multicast_ptr) and int(hp.buffer_ptrs[hp.rank]) == fp.data_ptr()
+                    and int(hg.buffer_ptrs[hg.rank]) == fg.data_ptr()):
+                out = (fp, fg, hp, hg)
+        except Exception:
+            out = None
+        return out if agree(out is not None) else None
 
     def zero_grad(self, set_to_none=True):
         """Always drops the gradients: a p.grad kept alive would alias the shared bucket (functional._bucket_for)."""
