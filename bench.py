@@ -852,7 +852,7 @@ def run_b200(args):
                                         if peer else
                                         'Adam, one fused multi-tensor launch (bnn_b200.FusedAdam, same update rule as torch.optim.Adam)')),
                             parallelism=f'MC samples sharded over {world} GPU(s), disjoint Philox sample indices'
-                                        + ((', gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory (bbb_adam_step_peer)'
+                                        + ((', gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory (bbb_adam_step_peer)' + (', gradient sum formed in the NVSwitch (multimem.ld_reduce) and parameters written with multimem.st' if getattr(opt, 'mc_g', 0) else '')
                                             if peer else ', per-layer NCCL all-reduce of the mu/rho gradients overlapped with the backward' + peer_note) if world > 1 else ''),
                             l2='flushed between timed steps (256 MiB write), flush outside the CUDA-event brackets',
                             step=graph_note, launches_per_step=launches_per_step,
