@@ -815,6 +815,11 @@ class _FusedELBOLR(torch.autograd.Function):
         sigma_p, S, beta, eps, nl = ctx.cfg
         if g_loss is None:
             return (None,) * (8 + 4 * nl)
+        if ctx.tf32 and getattr(ctx, 'consumed', False):
+            # the tcgen05 LR backward overwrites the saved delta buffers with dV (they have no other use in it)
+            raise RuntimeError('sample_elbo_lr: this graph was already differentiated (retain_graph=True is not supported '
+                               'by the TF32 local-reparameterisation path: its saved state is single-use)')
+        ctx.consumed = True
         sv = ctx.saved_tensors
         x2, d_out = sv[0], sv[1]
         params = [tuple(_f32c(t) for t in sv[2 + 4 * i:6 + 4 * i]) for i in range(nl)]

@@ -229,6 +229,35 @@ def test_large_batch_tf32_step_stores_post_activations(fake):
             assert (p.grad - q.grad).abs().max() <= 2e-5 * q.grad.abs().max() + 1e-7
 
 
+def test_second_backward_over_a_fused_graph_is_refused(fake):
+    """The fused ELBO's backward workspace is single-use (zero-filled by the forward, added into by the kernels), and the
+    TF32 LR backward overwrites its saved delta: retain_graph=True + a second backward raises instead of returning wrong
+    gradients.  The exact fp32 LR path keeps nothing single-use and may be differentiated twice."""
+    c = Case('small_cls_mix')
+    net = PC.build_net(c, 'cpu').train()
+    with bnn_b200.eps_mode('reference'):
+        torch.manual_seed(5)
+        loss = net.sample_elbo(c.x, c.y, c.beta, c.S)[0]
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match='already differentiated'):
+        loss.backward()
+    c = Case('small_lr_cls')
+    for tf32 in (True, False):
+        net = PC.build_net(c, 'cpu', tf32=tf32).train()
+        with bnn_b200.eps_mode('reference'):
+            torch.manual_seed(5)
+            loss = net.sample_elbo_lr(c.x, c.y, c.beta, c.S)[0]
+        loss.backward(retain_graph=True)
+        g1 = net.l1.weight_mu.grad.clone()
+        if tf32:
+            with pytest.raises(RuntimeError, match='already differentiated'):
+                loss.backward()
+        else:
+            net.zero_grad()
+            loss.backward()
+            assert torch.allclose(net.l1.weight_mu.grad, g1)
+
+
 def test_beta_may_be_a_tensor(fake):
     c = Case('small_cls_mix')
     outs = []
