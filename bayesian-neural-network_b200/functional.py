@@ -497,8 +497,9 @@ def _mlp_forward_call(x2, target, params, eps, prior, S, B, sigma, mode, need_gr
 
 
 class _FusedELBO(torch.autograd.Function):
-    """sample_elbo (networks.py:192-209) as 3 forward launches + likelihood + assembly; the
-    backward is 5 launches.  Only `loss` is differentiable."""
+    """sample_elbo (networks.py:192-209).  TF32 mode, batch <= 128: ONE C call per pass (bbb_mlp_fwd: a TMA-fed tcgen05
+    kernel per hidden layer + the fused head; bbb_mlp_bwd: head + one fused wgrad/dgrad kernel per layer).  Otherwise one
+    launch per layer (+ likelihood + assembly).  Only `loss` is differentiable."""
 
     @staticmethod
     def forward(ctx, x2, target, beta, S, sigma, mode, prior, tf32, fused_opt, *flat):
